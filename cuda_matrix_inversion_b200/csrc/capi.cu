@@ -1,0 +1,544 @@
+// capi.cu -- the C-ABI layer of libinvgpu.so: dispatch to the kernel tiers, the pinned-ring
+// host pipeline, and the reference's legacy-named entry points (include/inverse_gpu.h,
+// include/gauss_gpu.h).  No CPU fallback exists: every compute path launches a CUDA kernel.
+#include <errno.h>
+
+#include "engine.cuh"
+#include "generic_smem.cuh"
+#include "fast_tiers.cuh"
+
+#include "../../include/invgpu.h"
+#include "../../include/inverse_gpu.h"
+#include "../../include/gauss_gpu.h"
+
+namespace invgpu {
+
+std::atomic<long long> g_launches{0};
+
+std::mutex &engine_mutex() {
+    static std::mutex m;
+    return m;
+}
+
+DeviceState *device_state(int *err) {
+    static DeviceState states[64];
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) { *err = (int)e; return nullptr; }
+    if (dev < 0 || dev >= 64) { *err = INVGPU_EARG; return nullptr; }
+    DeviceState *ds = &states[dev];
+    if (ds->dev != dev) {
+        std::lock_guard<std::mutex> lk(engine_mutex());
+        if (ds->dev != dev) {
+            cudaDeviceProp p;
+            e = cudaGetDeviceProperties(&p, dev);
+            if (e != cudaSuccess) { *err = (int)e; return nullptr; }
+            ds->sms = p.multiProcessorCount;
+            ds->smem_optin = p.sharedMemPerBlockOptin;
+            ds->dev = dev;
+        }
+    }
+    return ds;
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel dispatch
+// ------------------------------------------------------------------------------------------
+#define INVGPU_LAUNCH(kern, block, smem, blocks_needed, ...)                                  \
+    do {                                                                                       \
+        int grid__ = 0;                                                                        \
+        int rc__ = persistent_grid(kern, block, smem, blocks_needed, ds, &grid__);             \
+        if (rc__ == -2) return INVGPU_EUNSUPPORTED;                                            \
+        if (rc__) return rc__;                                                                 \
+        kern<<<grid__, block, smem, st>>>(__VA_ARGS__);                                        \
+        g_launches.fetch_add(1, std::memory_order_relaxed);                                    \
+        return (int)cudaGetLastError();                                                        \
+    } while (0)
+
+template <typename T, typename IO, int STAGES>
+static int run_spd(IO io, int n, i64 batch, int *dInfo, cudaStream_t st) {
+    if (n < 1 || batch < 0) return INVGPU_EARG;
+    if (batch == 0) return 0;
+    int err = 0;
+    DeviceState *ds = device_state(&err);
+    if (!ds) return err;
+    int rc = fast_spd<T, IO, STAGES>(io, n, batch, dInfo, st, ds);
+    if (rc != INVGPU_NO_FAST_PATH) return rc;
+    if (n <= 32) {
+        INVGPU_LAUNCH((spd_generic_kernel<T, 32, IO, STAGES>), 128, 4 * (size_t)packed_row(n) * sizeof(T),
+                      (batch + 3) / 4, io, n, batch, dInfo);
+    } else if (n <= 128) {
+        INVGPU_LAUNCH((spd_generic_kernel<T, 128, IO, STAGES>), 128, (size_t)packed_row(n) * sizeof(T), batch,
+                      io, n, batch, dInfo);
+    } else if (n <= 256) {
+        INVGPU_LAUNCH((spd_generic_kernel<T, 256, IO, STAGES>), 256, (size_t)packed_row(n) * sizeof(T), batch,
+                      io, n, batch, dInfo);
+    }
+    return INVGPU_EUNSUPPORTED;
+}
+
+template <typename T, typename IO>
+static int run_general(IO io, int n, i64 batch, int *dInfo, cudaStream_t st) {
+    if (n < 1 || batch < 0) return INVGPU_EARG;
+    if (batch == 0) return 0;
+    int err = 0;
+    DeviceState *ds = device_state(&err);
+    if (!ds) return err;
+    int rc = fast_general<T, IO>(io, n, batch, dInfo, st, ds);
+    if (rc != INVGPU_NO_FAST_PATH) return rc;
+    const size_t slab = (size_t)n * (n | 1) * sizeof(T) + (size_t)n * sizeof(int);
+    if (n <= 32) {
+        INVGPU_LAUNCH((gj_generic_kernel<T, 32, IO>), 128, 4 * slab, (batch + 3) / 4, io, n, batch, dInfo);
+    } else if (n <= 128) {
+        INVGPU_LAUNCH((gj_generic_kernel<T, 128, IO>), 128, slab, batch, io, n, batch, dInfo);
+    } else if (n <= 256) {
+        INVGPU_LAUNCH((gj_generic_kernel<T, 256, IO>), 256, slab, batch, io, n, batch, dInfo);
+    }
+    return INVGPU_EUNSUPPORTED;
+}
+
+template <typename T>
+static int run_gp(GpIO<T> io, int n, i64 batch, int *dInfo, cudaStream_t st) {
+    if (n < 1 || batch < 0 || !io.a || !io.b || !io.c) return INVGPU_EARG;
+    if (!io.means && !io.variances) return INVGPU_EARG;
+    if (io.means && !io.d) return INVGPU_EARG;
+    if (io.variances && !io.e) return INVGPU_EARG;
+    if (batch == 0) return 0;
+    int err = 0;
+    DeviceState *ds = device_state(&err);
+    if (!ds) return err;
+    int rc = fast_gp<T>(io, n, batch, dInfo, st, ds);
+    if (rc != INVGPU_NO_FAST_PATH) return rc;
+    const size_t slab = ((size_t)packed_row(n) + 2 * (size_t)n) * sizeof(T);
+    if (n <= 32) {
+        INVGPU_LAUNCH((gp_generic_kernel<T, 32>), 128, 4 * slab, (batch + 3) / 4, io, n, batch, dInfo);
+    } else if (n <= 128) {
+        INVGPU_LAUNCH((gp_generic_kernel<T, 128>), 128, slab, batch, io, n, batch, dInfo);
+    } else if (n <= 256) {
+        INVGPU_LAUNCH((gp_generic_kernel<T, 256>), 256, slab, batch, io, n, batch, dInfo);
+    }
+    return INVGPU_EUNSUPPORTED;
+}
+
+template <typename T>
+static StridedIO<T> dense_io(const T *in, T *out, int n) {
+    StridedIO<T> io;
+    io.in = in; io.out = out;
+    io.in_stride = (i64)n * n; io.out_stride = (i64)n * n;
+    return io;
+}
+
+// ------------------------------------------------------------------------------------------
+// host pipeline: chunked H2D -> compute -> D2H over three streams and a 3-slot ring.
+// Pinned user buffers are DMA'd directly; pageable ones are staged through the pinned ring.
+// ------------------------------------------------------------------------------------------
+struct HostArr {
+    const char *in;     // host source (inputs) or nullptr
+    char *out;          // host destination (outputs) or nullptr
+    size_t unit;        // bytes per batch unit
+    bool pinned;
+    size_t off;         // offset of this array inside a slot
+};
+
+static bool is_pinned(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+static int ensure_pipeline(DeviceState *ds, size_t slot_bytes) {
+    if (!ds->streams_ready) {
+        INVGPU_TRY(cudaStreamCreateWithFlags(&ds->s_in, cudaStreamNonBlocking));
+        INVGPU_TRY(cudaStreamCreateWithFlags(&ds->s_comp, cudaStreamNonBlocking));
+        INVGPU_TRY(cudaStreamCreateWithFlags(&ds->s_out, cudaStreamNonBlocking));
+        for (int i = 0; i < DeviceState::kSlots; ++i) {
+            INVGPU_TRY(cudaEventCreateWithFlags(&ds->ev_in[i], cudaEventDisableTiming));
+            INVGPU_TRY(cudaEventCreateWithFlags(&ds->ev_comp[i], cudaEventDisableTiming));
+            INVGPU_TRY(cudaEventCreateWithFlags(&ds->ev_out[i], cudaEventDisableTiming));
+        }
+        ds->streams_ready = true;
+    }
+    if (ds->d_ws_bytes < slot_bytes) {
+        for (int i = 0; i < DeviceState::kSlots; ++i) {
+            if (ds->d_ws[i]) cudaFree(ds->d_ws[i]);
+            if (ds->h_ring[i]) cudaFreeHost(ds->h_ring[i]);
+            ds->d_ws[i] = nullptr; ds->h_ring[i] = nullptr;
+        }
+        ds->d_ws_bytes = 0; ds->h_ring_bytes = 0;
+        for (int i = 0; i < DeviceState::kSlots; ++i) {
+            INVGPU_TRY(cudaMalloc(&ds->d_ws[i], slot_bytes));
+            INVGPU_TRY(cudaHostAlloc(&ds->h_ring[i], slot_bytes, cudaHostAllocDefault));
+        }
+        ds->d_ws_bytes = slot_bytes; ds->h_ring_bytes = slot_bytes;
+    }
+    return 0;
+}
+
+static size_t g_chunk_bytes = 0;   // 0 = default; settable through INVGPU_CHUNK_MB
+
+// launch(dptrs, count, stream): dptrs[i] is the device address of array i for this chunk.
+template <typename LaunchFn>
+static int host_pipeline(std::vector<HostArr> &arrs, i64 batch, int *info, int *first_bad, LaunchFn launch) {
+    if (batch < 0) return INVGPU_EARG;
+    if (first_bad) *first_bad = -1;
+    if (batch == 0) return 0;
+    int err = 0;
+    DeviceState *ds = device_state(&err);
+    if (!ds) return err;
+    std::lock_guard<std::mutex> lk(engine_mutex());
+
+    // info rides along as one more output array (4 bytes per unit)
+    HostArr ia; ia.in = nullptr; ia.out = (char *)info; ia.unit = sizeof(int); ia.pinned = info && is_pinned(info); ia.off = 0;
+    arrs.push_back(ia);
+    size_t unit_total = 0;
+    for (auto &a : arrs) {
+        if (&a != &arrs.back()) a.pinned = is_pinned(a.in ? (const void *)a.in : (const void *)a.out);
+        unit_total += a.unit;
+    }
+    size_t target = g_chunk_bytes;
+    if (!target) {
+        const char *env = getenv("INVGPU_CHUNK_MB");
+        target = (env && atoi(env) > 0 ? (size_t)atoi(env) : 32) << 20;
+    }
+    i64 cu = (i64)(target / unit_total);
+    if (cu < 1) cu = 1;
+    if (cu > batch) cu = batch;
+    size_t slot_bytes = 0;
+    for (auto &a : arrs) { a.off = slot_bytes; slot_bytes += (a.unit * (size_t)cu + 255) & ~(size_t)255; }
+    int rc = ensure_pipeline(ds, slot_bytes);
+    if (rc) return rc;
+
+    const i64 nchunks = (batch + cu - 1) / cu;
+    const int S = DeviceState::kSlots;
+    auto drain = [&](i64 c) -> int {
+        const int slot = (int)(c % S);
+        INVGPU_TRY(cudaEventSynchronize(ds->ev_out[slot]));
+        const i64 first = c * cu;
+        const i64 cnt = (first + cu <= batch) ? cu : batch - first;
+        for (auto &a : arrs) {
+            if (a.in) continue;
+            const bool is_info = (&a == &arrs.back());
+            const char *ring = (const char *)ds->h_ring[slot] + a.off;
+            if (is_info) {
+                const int *ci = (const int *)ring;     // info is always staged through the ring
+                for (i64 i = 0; i < cnt; ++i) {
+                    if (ci[i] && first_bad && *first_bad < 0) { first_bad[0] = (int)(first + i); first_bad[1] = ci[i]; }
+                    if (info) info[first + i] = ci[i];
+                }
+            } else if (!a.pinned && a.out) {
+                memcpy(a.out + (size_t)first * a.unit, ring, (size_t)cnt * a.unit);
+            }
+        }
+        return 0;
+    };
+
+    for (i64 c = 0; c < nchunks; ++c) {
+        const int slot = (int)(c % S);
+        if (c >= S) { rc = drain(c - S); if (rc) return rc; }
+        const i64 first = c * cu;
+        const i64 cnt = (first + cu <= batch) ? cu : batch - first;
+        char *dbase = (char *)ds->d_ws[slot];
+        char *hbase = (char *)ds->h_ring[slot];
+        void *dptrs[16];
+        int na = 0;
+        for (auto &a : arrs) dptrs[na++] = dbase + a.off;
+        for (auto &a : arrs) {
+            if (!a.in) continue;
+            const char *src = a.in + (size_t)first * a.unit;
+            if (!a.pinned) { memcpy(hbase + a.off, src, (size_t)cnt * a.unit); src = hbase + a.off; }
+            INVGPU_TRY(cudaMemcpyAsync(dbase + a.off, src, (size_t)cnt * a.unit, cudaMemcpyHostToDevice, ds->s_in));
+        }
+        INVGPU_TRY(cudaEventRecord(ds->ev_in[slot], ds->s_in));
+        INVGPU_TRY(cudaStreamWaitEvent(ds->s_comp, ds->ev_in[slot], 0));
+        rc = launch(dptrs, cnt, ds->s_comp);
+        if (rc) return rc;
+        INVGPU_TRY(cudaEventRecord(ds->ev_comp[slot], ds->s_comp));
+        INVGPU_TRY(cudaStreamWaitEvent(ds->s_out, ds->ev_comp[slot], 0));
+        for (auto &a : arrs) {
+            if (a.in || (!a.out && &a != &arrs.back())) continue;
+            const bool is_info = (&a == &arrs.back());
+            char *dst = (a.pinned && !is_info) ? a.out + (size_t)first * a.unit : hbase + a.off;
+            INVGPU_TRY(cudaMemcpyAsync(dst, dbase + a.off, (size_t)cnt * a.unit, cudaMemcpyDeviceToHost, ds->s_out));
+        }
+        INVGPU_TRY(cudaEventRecord(ds->ev_out[slot], ds->s_out));
+    }
+    for (i64 c = (nchunks > S ? nchunks - S : 0); c < nchunks; ++c) { rc = drain(c); if (rc) return rc; }
+    return 0;
+}
+
+template <typename T, bool SPD>
+static int host_inverse(const T *As, T *aInvs, int n, i64 batch, int *info, int *first_bad) {
+    if (!As || !aInvs || n < 1) return INVGPU_EARG;
+    std::vector<HostArr> arrs(2);
+    arrs[0] = HostArr{(const char *)As, nullptr, (size_t)n * n * sizeof(T), false, 0};
+    arrs[1] = HostArr{nullptr, (char *)aInvs, (size_t)n * n * sizeof(T), false, 0};
+    return host_pipeline(arrs, batch, info, first_bad, [&](void **d, i64 cnt, cudaStream_t st) -> int {
+        StridedIO<T> io = dense_io<T>((const T *)d[0], (T *)d[1], n);
+        if (SPD) return run_spd<T, StridedIO<T>, SPD_INVERSE>(io, n, cnt, (int *)d[2], st);
+        return run_general<T, StridedIO<T>>(io, n, cnt, (int *)d[2], st);
+    });
+}
+
+template <typename T>
+static int host_gp(int n, const T *As, const T *Bs, const T *Cs, const T *Ds, const T *Es, T *Means, T *Vars,
+                   i64 batch, int *info, int *first_bad) {
+    if (!As || !Bs || !Cs || n < 1) return INVGPU_EARG;
+    if (!Means && !Vars) return INVGPU_EARG;
+    if ((Means && !Ds) || (Vars && !Es)) return INVGPU_EARG;
+    std::vector<HostArr> arrs;
+    arrs.push_back(HostArr{(const char *)As, nullptr, (size_t)n * sizeof(T), false, 0});
+    arrs.push_back(HostArr{(const char *)Bs, nullptr, (size_t)n * n * sizeof(T), false, 0});
+    arrs.push_back(HostArr{(const char *)Cs, nullptr, (size_t)n * sizeof(T), false, 0});
+    int iD = -1, iE = -1, iM = -1, iV = -1;
+    if (Means) { iD = (int)arrs.size(); arrs.push_back(HostArr{(const char *)Ds, nullptr, (size_t)n * sizeof(T), false, 0}); }
+    if (Vars)  { iE = (int)arrs.size(); arrs.push_back(HostArr{(const char *)Es, nullptr, sizeof(T), false, 0}); }
+    if (Means) { iM = (int)arrs.size(); arrs.push_back(HostArr{nullptr, (char *)Means, sizeof(T), false, 0}); }
+    if (Vars)  { iV = (int)arrs.size(); arrs.push_back(HostArr{nullptr, (char *)Vars, sizeof(T), false, 0}); }
+    const int iInfo = (int)arrs.size();
+    return host_pipeline(arrs, batch, info, first_bad, [&](void **d, i64 cnt, cudaStream_t st) -> int {
+        GpIO<T> io;
+        io.a = (const T *)d[0]; io.b = (const T *)d[1]; io.c = (const T *)d[2];
+        io.d = iD >= 0 ? (const T *)d[iD] : nullptr;
+        io.e = iE >= 0 ? (const T *)d[iE] : nullptr;
+        io.means = iM >= 0 ? (T *)d[iM] : nullptr;
+        io.variances = iV >= 0 ? (T *)d[iV] : nullptr;
+        return run_gp<T>(io, n, cnt, (int *)d[iInfo], st);
+    });
+}
+
+}  // namespace invgpu
+
+using namespace invgpu;
+
+template <typename T>
+static int spd_stages_ptrs(T *const *As, T *const *Outs, int n, int batch, int stages, int *dInfo, cudaStream_t s) {
+    if (!As || !Outs) return INVGPU_EARG;
+    PtrIO<T> io; io.in = As; io.out = Outs;
+    switch (stages) {
+        case SPD_INVERSE:           return run_spd<T, PtrIO<T>, SPD_INVERSE>(io, n, batch, dInfo, s);
+        case SPD_POTRF:             return run_spd<T, PtrIO<T>, SPD_POTRF>(io, n, batch, dInfo, s);
+        case SPD_TRTRI:             return run_spd<T, PtrIO<T>, SPD_TRTRI>(io, n, batch, dInfo, s);
+        case SPD_LAUUM:             return run_spd<T, PtrIO<T>, SPD_LAUUM>(io, n, batch, dInfo, s);
+        case SPD_POTRF | SPD_TRTRI: return run_spd<T, PtrIO<T>, SPD_POTRF | SPD_TRTRI>(io, n, batch, dInfo, s);
+        case SPD_TRTRI | SPD_LAUUM: return run_spd<T, PtrIO<T>, SPD_TRTRI | SPD_LAUUM>(io, n, batch, dInfo, s);
+        default: return INVGPU_EARG;
+    }
+}
+
+// ==========================================================================================
+// extended C ABI (include/invgpu.h)
+// ==========================================================================================
+extern "C" {
+
+const char *invgpu_version(void) { return "invgpu 0.1 (sm_100a)"; }
+
+int invgpu_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+const char *invgpu_error_string(int code) {
+    if (code == 0) return "success";
+    if (code == INVGPU_EARG) return "invalid argument";
+    if (code == INVGPU_EUNSUPPORTED) return "matrix dimension not supported by this path";
+    if (code == INVGPU_ESINGULAR) return "a matrix of the batch is singular / not positive definite";
+    if (code > 0) return cudaGetErrorString((cudaError_t)code);
+    return "unknown error";
+}
+
+invgpu_i64 invgpu_launch_count(void) { return g_launches.load(); }
+
+const char *invgpu_tier_name(int op, int n, int dtype_bytes) { return fast_tier_name(op, n, dtype_bytes); }
+
+int invgpu_spd_inverse_f32(const float *dA, float *dAinv, int n, invgpu_i64 batch, int *dInfo, invgpu_stream_t s) {
+    if (!dA || !dAinv) return INVGPU_EARG;
+    return run_spd<float, StridedIO<float>, SPD_INVERSE>(dense_io<float>(dA, dAinv, n), n, batch, dInfo, (cudaStream_t)s);
+}
+int invgpu_spd_inverse_f64(const double *dA, double *dAinv, int n, invgpu_i64 batch, int *dInfo, invgpu_stream_t s) {
+    if (!dA || !dAinv) return INVGPU_EARG;
+    return run_spd<double, StridedIO<double>, SPD_INVERSE>(dense_io<double>(dA, dAinv, n), n, batch, dInfo, (cudaStream_t)s);
+}
+int invgpu_spd_factor_f32(const float *dA, float *dL, int n, invgpu_i64 batch, int *dInfo, invgpu_stream_t s) {
+    if (!dA || !dL) return INVGPU_EARG;
+    return run_spd<float, StridedIO<float>, SPD_POTRF>(dense_io<float>(dA, dL, n), n, batch, dInfo, (cudaStream_t)s);
+}
+int invgpu_spd_factor_f64(const double *dA, double *dL, int n, invgpu_i64 batch, int *dInfo, invgpu_stream_t s) {
+    if (!dA || !dL) return INVGPU_EARG;
+    return run_spd<double, StridedIO<double>, SPD_POTRF>(dense_io<double>(dA, dL, n), n, batch, dInfo, (cudaStream_t)s);
+}
+int invgpu_general_inverse_f32(const float *dA, float *dAinv, int n, invgpu_i64 batch, int *dInfo, invgpu_stream_t s) {
+    if (!dA || !dAinv) return INVGPU_EARG;
+    return run_general<float, StridedIO<float>>(dense_io<float>(dA, dAinv, n), n, batch, dInfo, (cudaStream_t)s);
+}
+int invgpu_general_inverse_f64(const double *dA, double *dAinv, int n, invgpu_i64 batch, int *dInfo, invgpu_stream_t s) {
+    if (!dA || !dAinv) return INVGPU_EARG;
+    return run_general<double, StridedIO<double>>(dense_io<double>(dA, dAinv, n), n, batch, dInfo, (cudaStream_t)s);
+}
+
+int invgpu_spd_stages_ptrs_f32(float *const *As, float *const *Outs, int n, int batch, int stages, int *dInfo, invgpu_stream_t s) {
+    return spd_stages_ptrs<float>(As, Outs, n, batch, stages, dInfo, (cudaStream_t)s);
+}
+int invgpu_spd_stages_ptrs_f64(double *const *As, double *const *Outs, int n, int batch, int stages, int *dInfo, invgpu_stream_t s) {
+    return spd_stages_ptrs<double>(As, Outs, n, batch, stages, dInfo, (cudaStream_t)s);
+}
+int invgpu_general_inverse_ptrs_f32(float *const *As, float *const *Ainvs, int n, int batch, int *dInfo, invgpu_stream_t s) {
+    if (!As || !Ainvs) return INVGPU_EARG;
+    PtrIO<float> io; io.in = As; io.out = Ainvs;
+    return run_general<float, PtrIO<float>>(io, n, batch, dInfo, (cudaStream_t)s);
+}
+int invgpu_general_inverse_ptrs_f64(double *const *As, double *const *Ainvs, int n, int batch, int *dInfo, invgpu_stream_t s) {
+    if (!As || !Ainvs) return INVGPU_EARG;
+    PtrIO<double> io; io.in = As; io.out = Ainvs;
+    return run_general<double, PtrIO<double>>(io, n, batch, dInfo, (cudaStream_t)s);
+}
+
+int invgpu_gp_f32(int n, const float *dA, const float *dB, const float *dC, const float *dD, const float *dE,
+                  float *dMeans, float *dVariances, invgpu_i64 batch, int *dInfo, invgpu_stream_t s) {
+    GpIO<float> io{dA, dB, dC, dD, dE, dMeans, dVariances};
+    return run_gp<float>(io, n, batch, dInfo, (cudaStream_t)s);
+}
+int invgpu_gp_f64(int n, const double *dA, const double *dB, const double *dC, const double *dD, const double *dE,
+                  double *dMeans, double *dVariances, invgpu_i64 batch, int *dInfo, invgpu_stream_t s) {
+    GpIO<double> io{dA, dB, dC, dD, dE, dMeans, dVariances};
+    return run_gp<double>(io, n, batch, dInfo, (cudaStream_t)s);
+}
+
+static int finish_host(int rc, const int *info, const int *bad) {
+    if (rc) return rc;
+    if (!info && bad[0] >= 0) return INVGPU_ESINGULAR;
+    return 0;
+}
+int invgpu_spd_inverse_host_f32(const float *As, float *aInvs, int n, invgpu_i64 batch, int *info) {
+    int bad[2]; return finish_host(host_inverse<float, true>(As, aInvs, n, batch, info, bad), info, bad);
+}
+int invgpu_spd_inverse_host_f64(const double *As, double *aInvs, int n, invgpu_i64 batch, int *info) {
+    int bad[2]; return finish_host(host_inverse<double, true>(As, aInvs, n, batch, info, bad), info, bad);
+}
+int invgpu_general_inverse_host_f32(const float *As, float *aInvs, int n, invgpu_i64 batch, int *info) {
+    int bad[2]; return finish_host(host_inverse<float, false>(As, aInvs, n, batch, info, bad), info, bad);
+}
+int invgpu_general_inverse_host_f64(const double *As, double *aInvs, int n, invgpu_i64 batch, int *info) {
+    int bad[2]; return finish_host(host_inverse<double, false>(As, aInvs, n, batch, info, bad), info, bad);
+}
+int invgpu_gp_host_f32(int n, const float *As, const float *Bs, const float *Cs, const float *Ds, const float *Es,
+                       float *Means, float *Variances, invgpu_i64 batch, int *info) {
+    int bad[2]; return finish_host(host_gp<float>(n, As, Bs, Cs, Ds, Es, Means, Variances, batch, info, bad), info, bad);
+}
+int invgpu_gp_host_f64(int n, const double *As, const double *Bs, const double *Cs, const double *Ds, const double *Es,
+                       double *Means, double *Variances, invgpu_i64 batch, int *info) {
+    int bad[2]; return finish_host(host_gp<double>(n, As, Bs, Cs, Ds, Es, Means, Variances, batch, info, bad), info, bad);
+}
+
+void *invgpu_host_alloc(unsigned long long bytes) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void invgpu_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+void invgpu_release_workspace(void) {
+    int err = 0;
+    DeviceState *ds = device_state(&err);
+    if (!ds) return;
+    std::lock_guard<std::mutex> lk(engine_mutex());
+    cudaDeviceSynchronize();
+    for (int i = 0; i < DeviceState::kSlots; ++i) {
+        if (ds->d_ws[i]) cudaFree(ds->d_ws[i]);
+        if (ds->h_ring[i]) cudaFreeHost(ds->h_ring[i]);
+        ds->d_ws[i] = nullptr; ds->h_ring[i] = nullptr;
+    }
+    ds->d_ws_bytes = 0; ds->h_ring_bytes = 0;
+}
+
+// ==========================================================================================
+// legacy-named entry points (include/inverse_gpu.h, include/gauss_gpu.h)
+// Error convention of the reference: message on stderr, then exit (include/helper_cpu.h:12-21,
+// include/helper_gpu.h:9-18).
+// ==========================================================================================
+static void legacy_check(int rc, const char *what, const int *bad, const char *singular_fmt) {
+    if (rc > 0) {
+        fprintf(stderr, "GPUassert: %s %s (%s)\n", cudaGetErrorString((cudaError_t)rc), __FILE__, what);
+        cudaDeviceReset();
+        exit(rc);
+    }
+    if (rc < 0) {
+        fprintf(stderr, "ENSURE FAILED %s (%s)\r\n%s\r\n", __FILE__, what, invgpu_error_string(rc));
+        exit(EXIT_FAILURE);
+    }
+    if (bad && bad[0] >= 0) {
+        fprintf(stderr, "ENSURE FAILED %s (%s, matrix %d)\r\n", __FILE__, what, bad[0]);
+        fprintf(stderr, singular_fmt, bad[1]);
+        fprintf(stderr, "\r\n");
+        exit(EXIT_FAILURE);
+    }
+}
+
+static const char *kCholMsg = "Error code %d in cholesky factorization";   // reference src/inverse.c:94
+static const char *kLuMsg = "Error code %d in LU-decomposition";           // reference src/inverse.c:64
+
+#define LEGACY_HOST_SPD(name)                                                                   \
+    void name(cublasHandle_t, int n, Array As, Array aInvs, int batchSize) {                    \
+        int bad[2];                                                                             \
+        int rc = host_inverse<float, true>(As, aInvs, n, batchSize, nullptr, bad);              \
+        legacy_check(rc, #name, bad, kCholMsg);                                                 \
+    }
+LEGACY_HOST_SPD(inverse_cholesky_batched_gpu)
+LEGACY_HOST_SPD(inverse_cholesky_mm_batched_gpu)
+LEGACY_HOST_SPD(inverse_cholesky_mm2_batched_gpu)
+LEGACY_HOST_SPD(inverse_cholesky_stride_batched_gpu)
+
+#define LEGACY_HOST_GENERAL(name)                                                               \
+    void name(cublasHandle_t, int n, Array As, Array aInvs, int batchSize) {                    \
+        int bad[2];                                                                             \
+        int rc = host_inverse<float, false>(As, aInvs, n, batchSize, nullptr, bad);             \
+        legacy_check(rc, #name, bad, kLuMsg);                                                   \
+    }
+LEGACY_HOST_GENERAL(inverse_gauss_batched_gpu)
+LEGACY_HOST_GENERAL(inverse_lu_cuda_batched_gpu)
+
+// device flavours: asynchronous on the legacy default stream, no flag check (the reference's
+// hand-written kernels detect nothing either, src/gauss/batched_invert.cu:29-32).
+#define LEGACY_DEVICE_SPD(name, IN, OUT, STAGES)                                                \
+    void name(cublasHandle_t, int N, Array *devAs, Array *devAInvs, int batchSize) {            \
+        (void)devAs; (void)devAInvs;                                                            \
+        int rc = invgpu_spd_stages_ptrs_f32(IN, OUT, N, batchSize, STAGES, nullptr, nullptr);   \
+        legacy_check(rc, #name, nullptr, kCholMsg);                                             \
+    }
+LEGACY_DEVICE_SPD(inverse_cholesky_batched_device, devAs, devAInvs, SPD_INVERSE)
+LEGACY_DEVICE_SPD(inverse_cholesky_mm_batched_device, devAs, devAInvs, SPD_INVERSE)
+LEGACY_DEVICE_SPD(inverse_cholesky_mm2_batched_device, devAs, devAInvs, SPD_INVERSE)
+LEGACY_DEVICE_SPD(decompose_cholesky_batched_device, devAs, devAs, SPD_POTRF)
+LEGACY_DEVICE_SPD(decompose_cholesky_mm_batched_device, devAs, devAs, SPD_POTRF)
+LEGACY_DEVICE_SPD(decompose_cholesky_stride_batched_device, devAInvs, devAInvs, SPD_POTRF)
+LEGACY_DEVICE_SPD(inverse_upper_stride_batched_device, devAInvs, devAInvs, SPD_TRTRI)
+LEGACY_DEVICE_SPD(multiply_upper_stride_batched_device, devAInvs, devAInvs, SPD_LAUUM)
+LEGACY_DEVICE_SPD(inverse_cholesky_stride_batched_device, devAInvs, devAInvs, SPD_INVERSE)
+
+void inverse_gauss_batched_device(cublasHandle_t, int N, Array *devAs, Array *devAInvs, int batchSize) {
+    int rc = invgpu_general_inverse_ptrs_f32(devAs, devAInvs, N, batchSize, nullptr, nullptr);
+    legacy_check(rc, "inverse_gauss_batched_device", nullptr, kLuMsg);
+}
+void inverse_lu_cuda_batched_device(cublasHandle_t, int N, Array *devAs, Array *devAInvs, int batchSize) {
+    int rc = invgpu_general_inverse_ptrs_f32(devAs, devAInvs, N, batchSize, nullptr, nullptr);
+    legacy_check(rc, "inverse_lu_cuda_batched_device", nullptr, kLuMsg);
+}
+
+void calcluateMeanGPU(int n, Array As, Array Bs, Array Cs, Array Ds, Array Means, int batchSize) {
+    int bad[2];
+    int rc = host_gp<float>(n, As, Bs, Cs, Ds, nullptr, Means, nullptr, batchSize, nullptr, bad);
+    legacy_check(rc, "calcluateMeanGPU", bad, kCholMsg);
+}
+void calcluateVarianceGPU(int n, Array As, Array Bs, Array Cs, Array Es, Array Variances, int batchSize) {
+    int bad[2];
+    int rc = host_gp<float>(n, As, Bs, Cs, nullptr, Es, nullptr, Variances, batchSize, nullptr, bad);
+    legacy_check(rc, "calcluateVarianceGPU", bad, kCholMsg);
+}
+void calcluateMeanSolveGPU(int n, Array As, Array Bs, Array Cs, Array Ds, Array Means, int batchSize) {
+    calcluateMeanGPU(n, As, Bs, Cs, Ds, Means, batchSize);
+}
+void calcluateVarianceSolveGPU(int n, Array As, Array Bs, Array Cs, Array Es, Array Variances, int batchSize) {
+    calcluateVarianceGPU(n, As, Bs, Cs, Es, Variances, batchSize);
+}
+
+}  // extern "C"

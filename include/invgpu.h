@@ -1,0 +1,112 @@
+/* invgpu.h -- extended C ABI of the B200 batched dense-inversion engine (libinvgpu.so).
+ *
+ * Everything the legacy-named symbols (inverse_gpu.h, gauss_gpu.h) do is a thin wrapper over
+ * these entry points.  Plain pointers and sizes only; no C++ or torch types.  Each entry
+ * point cites the reference interface (file:line under /root/reference) it replaces.
+ *
+ * Conventions
+ *   - matrices are column-major, lda = n; "dense" batches are back to back (matrix k at
+ *     base + k*n*n), exactly what readMatricesFile produces (src/helper.cu:45).
+ *   - `_f32` / `_f64` select the arithmetic type (the reference is fp32 only, types.h:4).
+ *   - device-flavour calls are ASYNCHRONOUS on `stream` (a cudaStream_t passed as void*,
+ *     NULL = legacy default stream) and never synchronise.
+ *   - info (may be NULL): one int per matrix, LAPACK semantics.  SPD paths: spotrf info
+ *     (k > 0: leading minor of order k is not positive definite).  General path: sgetrf info
+ *     (k > 0: pivot k is exactly zero).  A flagged matrix's output is left unwritten; the
+ *     rest of the batch is processed normally (the reference aborts the process instead,
+ *     src/inverse.c:94, src/gauss/inverse_gpu.cu:36).
+ *   - return value: 0 on success, a positive cudaError_t, or a negative INVGPU_E* code.
+ *   - there is NO CPU fallback anywhere: without a CUDA device every compute call fails.
+ */
+#ifndef INVGPU_H
+#define INVGPU_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define INVGPU_EARG         (-1)   /* bad argument (n < 1, batch < 0, null pointer) */
+#define INVGPU_EUNSUPPORTED (-2)   /* n beyond what the selected path supports */
+#define INVGPU_ESINGULAR    (-3)   /* host-flavour call without info[]: some matrix was flagged */
+
+#define INVGPU_MAX_N_SPD_F32     256
+#define INVGPU_MAX_N_SPD_F64     128   /* 256 in fp64 does not fit one CTA's shared memory */
+#define INVGPU_MAX_N_GENERAL_F32 128
+#define INVGPU_MAX_N_GENERAL_F64 128
+
+typedef void *invgpu_stream_t;
+typedef long long invgpu_i64;
+
+/* ---- library / device ------------------------------------------------------------------ */
+const char *invgpu_version(void);
+int invgpu_device_count(void);                 /* 0 when no CUDA device is usable */
+const char *invgpu_error_string(int code);
+/* number of kernels launched by this library on the calling thread's device since load
+ * (used by bench.py's `gpu_launches`). */
+invgpu_i64 invgpu_launch_count(void);
+/* name of the kernel tier the dispatcher picks for (op, n, dtype_bytes): "warp", "cta", "generic" */
+const char *invgpu_tier_name(int op, int n, int dtype_bytes);
+
+/* ---- SPD inverse, dense strided device batches ------------------------------------------ *
+ * A^-1 via Cholesky potrf -> trtri -> lauum; reads the upper triangle, writes both.
+ * Replaces inverse_cholesky_batched_device & co (src/inverse_cholesky_gpu.cu:323-354,
+ * 607-623, 692-696) and the CPU path inverse_chol_blas (src/inverse.c:89-98). */
+int invgpu_spd_inverse_f32(const float *dA, float *dAinv, int n, invgpu_i64 batch, int *dInfo, invgpu_stream_t stream);
+int invgpu_spd_inverse_f64(const double *dA, double *dAinv, int n, invgpu_i64 batch, int *dInfo, invgpu_stream_t stream);
+
+/* Cholesky factor only: dL = lower factor, strictly upper zeroed (may alias dA).
+ * Replaces decompose_cholesky_batched_device (src/inverse_cholesky_gpu.cu:356-369). */
+int invgpu_spd_factor_f32(const float *dA, float *dL, int n, invgpu_i64 batch, int *dInfo, invgpu_stream_t stream);
+int invgpu_spd_factor_f64(const double *dA, double *dL, int n, invgpu_i64 batch, int *dInfo, invgpu_stream_t stream);
+
+/* ---- general inverse, dense strided device batches -------------------------------------- *
+ * In-place Gauss-Jordan with partial pivoting.  Replaces `invert`
+ * (src/gauss/batched_invert.cu:84-95) and the cuBLAS getrf/getriBatched pair
+ * (src/gauss/inverse_gpu.cu:24-50). */
+int invgpu_general_inverse_f32(const float *dA, float *dAinv, int n, invgpu_i64 batch, int *dInfo, invgpu_stream_t stream);
+int invgpu_general_inverse_f64(const double *dA, double *dAinv, int n, invgpu_i64 batch, int *dInfo, invgpu_stream_t stream);
+
+/* ---- pointer-array flavour (reference `Array *devAs`) ------------------------------------ *
+ * As[k] / Ainvs[k] are device pointers; the arrays may be in pinned-host or device memory.
+ * stages: bit mask 1 = potrf, 2 = trtri, 4 = lauum (7 = full inverse, 1 = factor);
+ * As == Ainvs (in place) is allowed. */
+int invgpu_spd_stages_ptrs_f32(float *const *As, float *const *Outs, int n, int batch, int stages, int *dInfo, invgpu_stream_t stream);
+int invgpu_spd_stages_ptrs_f64(double *const *As, double *const *Outs, int n, int batch, int stages, int *dInfo, invgpu_stream_t stream);
+int invgpu_general_inverse_ptrs_f32(float *const *As, float *const *Ainvs, int n, int batch, int *dInfo, invgpu_stream_t stream);
+int invgpu_general_inverse_ptrs_f64(double *const *As, double *const *Ainvs, int n, int batch, int *dInfo, invgpu_stream_t stream);
+
+/* ---- fused GP mean / variance, dense device batches -------------------------------------- *
+ * means[i] = A_i^T (B_i + diag C_i)^-1 D_i ; variances[i] = E_i - A_i^T (B_i + diag C_i)^-1 A_i.
+ * ONE kernel replaces addDiagonal -> batchedInverse -> batchedMul -> batchedMul
+ * (src/gauss_bench.cu:38,68,87,127-265,275-409).  dD/dMeans or dE/dVariances may be NULL to
+ * compute only the other quantity; with both present the factorisation is shared. */
+int invgpu_gp_f32(int n, const float *dA, const float *dB, const float *dC, const float *dD, const float *dE,
+                  float *dMeans, float *dVariances, invgpu_i64 batch, int *dInfo, invgpu_stream_t stream);
+int invgpu_gp_f64(int n, const double *dA, const double *dB, const double *dC, const double *dD, const double *dE,
+                  double *dMeans, double *dVariances, invgpu_i64 batch, int *dInfo, invgpu_stream_t stream);
+
+/* ---- host flavour with per-matrix info --------------------------------------------------- *
+ * Same contract as the reference's *_gpu wrappers (host pointers, synchronous, H2D + compute
+ * + D2H inside the call; e.g. src/gauss/batched_invert.cu:99-177) but chunked and pipelined
+ * over a persistent pinned ring instead of per-call cudaHostAlloc/cudaMallocPitch/cudaFree.
+ * info may be NULL (then a flagged matrix makes the call return INVGPU_ESINGULAR). */
+int invgpu_spd_inverse_host_f32(const float *As, float *aInvs, int n, invgpu_i64 batch, int *info);
+int invgpu_spd_inverse_host_f64(const double *As, double *aInvs, int n, invgpu_i64 batch, int *info);
+int invgpu_general_inverse_host_f32(const float *As, float *aInvs, int n, invgpu_i64 batch, int *info);
+int invgpu_general_inverse_host_f64(const double *As, double *aInvs, int n, invgpu_i64 batch, int *info);
+int invgpu_gp_host_f32(int n, const float *As, const float *Bs, const float *Cs, const float *Ds, const float *Es,
+                       float *Means, float *Variances, invgpu_i64 batch, int *info);
+int invgpu_gp_host_f64(int n, const double *As, const double *Bs, const double *Cs, const double *Ds, const double *Es,
+                       double *Means, double *Variances, invgpu_i64 batch, int *info);
+
+/* pinned host allocations for callers that want the zero-staging fast path of the host flavour */
+void *invgpu_host_alloc(unsigned long long bytes);
+void invgpu_host_free(void *p);
+/* drop the cached device workspace / pinned ring of the calling thread's device */
+void invgpu_release_workspace(void);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* INVGPU_H */

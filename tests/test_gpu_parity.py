@@ -1,0 +1,447 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle on the
+same inputs, against the reference's golden fixtures, and -- at BASELINE.json's full sizes --
+through size-independent properties.  Tolerances are the north_star's: normwise relative error
+and residual ||A A^-1 - I||_inf <= 1e-4 in fp32 and <= 1e-10 in fp64 (see tests/util.py)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import oracle as orc
+from tests.util import (TOL, general_batch, gp_batch, load_fixture, normwise_err, residual_inf, spd_batch)
+
+pytestmark = pytest.mark.gpu
+
+DTYPES = [np.float32, np.float64]
+
+
+@pytest.fixture(scope="module")
+def api():
+    from cuda_matrix_inversion_b200 import api as _api
+    assert _api.device_count() > 0, "no CUDA device: the product has no CPU fallback"
+    return _api
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch as _t
+    assert _t.cuda.is_available()
+    return _t
+
+
+# --------------------------------------------------------------------------------------- SPD inverse
+@pytest.mark.parametrize("n", [8, 16, 32, 64])
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_spd_inverse_reference_fixtures(api, fixtures_dir, n, dtype):
+    a = load_fixture(fixtures_dir, f"inverse_100_{n}x{n}/a.mats", dtype)
+    flat = orc.to_colmajor(a)
+    launches = api.launch_count()
+    got, info = api.spd_inverse_host(flat, n)
+    assert api.launch_count() > launches, "no CUDA kernel was launched"
+    assert not info.any()
+    want, oinfo = orc.chol_inverse(flat, n)
+    assert not oinfo.any()
+    tol = TOL[np.dtype(dtype)]
+    got3, want3 = orc.from_colmajor(got, n), orc.from_colmajor(want, n)
+    assert normwise_err(got3, want3) <= tol
+    assert residual_inf(a, got3) <= tol
+    assert np.abs(got3 - got3.transpose(0, 2, 1)).max() <= tol * np.abs(got3).max()   # both triangles written
+    gold = os.path.join(fixtures_dir, f"inverse_100_{n}x{n}/aInv.mats")
+    if os.path.exists(gold):   # 4-digit MATLAB goldens pin to ~1e-4 absolute
+        assert np.abs(got3 - orc.read_mats(gold, np.float64)).max() < 2e-4
+
+
+def test_spd_inverse_known_answer(api, fixtures_dir):
+    a = load_fixture(fixtures_dir, "simpleMean/chol.mats", np.float64)
+    want = load_fixture(fixtures_dir, "simpleMean/cholinv.mats", np.float64)
+    for dtype, tol in ((np.float64, 1e-10), (np.float32, 2e-4)):      # cond ~ 1185
+        got, info = api.spd_inverse_host(orc.to_colmajor(a.astype(dtype)), 4)
+        assert info[0] == 0
+        assert np.abs(orc.from_colmajor(got, 4)[0] - want[0]).max() <= max(tol, 1e-5)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 7, 8, 13, 16, 24, 31, 32, 33, 47, 64, 96, 100, 128])
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_spd_inverse_sizes(api, n, dtype):
+    batch = 67 if n <= 32 else 19
+    a = spd_batch(n, batch, dtype, seed=100 + n)
+    flat = orc.to_colmajor(a)
+    got, info = api.spd_inverse_host(flat, n)
+    want, _ = orc.chol_inverse(flat, n)
+    assert not info.any()
+    tol = TOL[np.dtype(dtype)]
+    assert normwise_err(orc.from_colmajor(got, n), orc.from_colmajor(want, n)) <= tol
+    assert residual_inf(a, orc.from_colmajor(got, n)) <= tol
+
+
+@pytest.mark.parametrize("n", [160, 200, 256])
+def test_spd_inverse_256_bucket_fp32(api, n):
+    a = spd_batch(n, 5, np.float32, seed=7)
+    flat = orc.to_colmajor(a)
+    got, info = api.spd_inverse_host(flat, n)
+    want, _ = orc.chol_inverse(flat, n)
+    assert not info.any()
+    assert normwise_err(orc.from_colmajor(got, n), orc.from_colmajor(want, n)) <= 1e-4
+    assert residual_inf(a, orc.from_colmajor(got, n)) <= 1e-4
+
+
+def test_spd_reads_upper_triangle_only(api):
+    """spotrf_("U") semantics (reference src/inverse.c:92): garbage below the diagonal is ignored."""
+    n = 16
+    a = spd_batch(n, 9, np.float64, seed=3)
+    dirty = a.copy()
+    il = np.tril_indices(n, -1)
+    dirty[:, il[0], il[1]] = 1e30
+    got, info = api.spd_inverse_host(orc.to_colmajor(dirty), n)
+    want, _ = api.spd_inverse_host(orc.to_colmajor(a), n)
+    assert not info.any()
+    np.testing.assert_array_equal(got, want)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_spd_flags_match_oracle(api, fixtures_dir, dtype):
+    n = 8
+    a = spd_batch(n, 12, np.float64, seed=11)
+    a[2] = np.diag([4.0, 3.0, -1.0, 2.0, 1, 1, 1, 1])            # indefinite: info 3
+    a[5, 6, 6] = np.nan                                          # NaN pivot: info 7
+    a[7] = 1.1                                                    # rank one: info 2
+    a[9] = -np.eye(n)                                             # negative definite: info 1
+    flat = orc.to_colmajor(a.astype(dtype))
+    sentinel = np.full_like(flat, 777.0)
+    got, info = api.spd_inverse_host(flat, n, out=sentinel.copy())
+    want, oinfo = orc.chol_inverse(flat, n)
+    np.testing.assert_array_equal(info, oinfo)
+    assert info[2] == 3 and info[5] == 7 and info[7] == 2 and info[9] == 1
+    good = info == 0
+    tol = TOL[np.dtype(dtype)]
+    assert normwise_err(orc.from_colmajor(got, n)[good], orc.from_colmajor(want, n)[good]) <= tol
+    # flagged matrices are left unwritten, the rest of the batch is processed
+    assert (orc.from_colmajor(got, n)[~good] == 777.0).all()
+    # the reference's own singular fixture (simpleMean/b.mats, all 1.1)
+    b = load_fixture(fixtures_dir, "simpleMean/b.mats", dtype)
+    _, info = api.spd_inverse_host(orc.to_colmajor(b), 2)
+    assert info[0] == 2
+
+
+@pytest.mark.parametrize("n", [4, 16, 33, 64])
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_spd_factor(api, torch, n, dtype):
+    a = spd_batch(n, 21, dtype, seed=5)
+    tdt = torch.float32 if dtype == np.float32 else torch.float64
+    d_a = torch.from_numpy(orc.to_colmajor(a)).cuda()
+    d_l = torch.empty_like(d_a)
+    d_info = torch.full((21,), -1, dtype=torch.int32, device="cuda")
+    api.spd_factor_device(d_a.data_ptr(), d_l.data_ptr(), n, 21, dtype, d_info.data_ptr(),
+                          torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert not d_info.cpu().numpy().any()
+    l = orc.from_colmajor(d_l.cpu().numpy(), n).astype(np.float64)
+    assert np.abs(np.triu(l, 1)).max() == 0
+    want = np.linalg.cholesky(a.astype(np.float64))
+    assert normwise_err(l, want) <= TOL[np.dtype(dtype)]
+    assert tdt == d_l.dtype
+
+
+# --------------------------------------------------------------------------------------- general inverse
+@pytest.mark.parametrize("n", [8, 16, 32, 64, 128])
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_general_inverse_reference_fixtures(api, fixtures_dir, n, dtype):
+    a = load_fixture(fixtures_dir, f"square_5_{n}_{n}.mats", dtype)
+    flat = orc.to_colmajor(a)
+    got, info = api.general_inverse_host(flat, n)
+    want, oinfo = orc.gauss_jordan_inverse(flat, n)
+    assert not info.any() and not oinfo.any()
+    got3, want3 = orc.from_colmajor(got, n), orc.from_colmajor(want, n)
+    exact = np.linalg.inv(a.astype(np.float64))
+    cond = np.linalg.cond(a.astype(np.float64)).max()
+    eps = np.finfo(dtype).eps
+    # these fixtures have cond up to 9e3: the stated tolerance applies where cond*eps allows it,
+    # and in every case the CUDA result must be as close to the truth as the oracle's is.
+    bound = max(TOL[np.dtype(dtype)], 16 * eps * cond)
+    assert normwise_err(got3, exact) <= bound
+    assert normwise_err(got3, want3) <= bound
+    assert residual_inf(a, got3) <= max(TOL[np.dtype(dtype)], 64 * eps * cond)
+
+
+def test_general_inverse_square_100_64_64_regenerated(api, golden_dir):
+    """BASELINE config 2: square_100_64_64.mats is missing from the reference mount
+    (.MISSING_LARGE_BLOBS); tests/golden/make_square_100_64_64.py regenerates it."""
+    p = os.path.join(golden_dir, "square_100_64_64.npz")
+    a = np.load(p)["a"]                         # [100, 64, 64] float32
+    from tests.golden.make_square_100_64_64 import generate
+    np.testing.assert_array_equal(a, generate())       # the committed fixture is what the script makes
+    inv64 = np.linalg.inv(a.astype(np.float64))
+    cond = np.linalg.cond(a.astype(np.float64))
+    flat = orc.to_colmajor(a)
+    got, info = api.general_inverse_host(flat, 64)
+    assert not info.any()
+    got3 = orc.from_colmajor(got, 64)
+    err = np.abs(got3 - inv64).reshape(100, -1).max(1) / np.abs(inv64).reshape(100, -1).max(1)
+    assert (err <= np.maximum(1e-4, 16 * np.finfo(np.float32).eps * cond)).all()
+    want, _ = orc.gauss_jordan_inverse(flat, 64)
+    ok = cond < 500
+    assert ok.sum() > 10
+    assert normwise_err(got3[ok], orc.from_colmajor(want, 64)[ok]) <= 1e-4
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 7, 13, 31, 33, 50, 100])
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_general_inverse_sizes(api, n, dtype):
+    rng = np.random.default_rng(n)
+    a = (rng.random((23, n, n)) + np.eye(n) * 0.5).astype(dtype)
+    a[:, 0, 0] = 0.0          # force a row interchange in step 0 (when n > 1)
+    if n == 1:
+        a[:, 0, 0] = 2.0
+    flat = orc.to_colmajor(a)
+    got, info = api.general_inverse_host(flat, n)
+    want, oinfo = orc.gauss_jordan_inverse(flat, n)
+    np.testing.assert_array_equal(info, oinfo)
+    assert not info.any()
+    cond = np.linalg.cond(a.astype(np.float64)).max()
+    bound = max(TOL[np.dtype(dtype)], 16 * np.finfo(dtype).eps * cond)
+    assert normwise_err(orc.from_colmajor(got, n), orc.from_colmajor(want, n)) <= bound
+    assert residual_inf(a, orc.from_colmajor(got, n)) <= 4 * bound
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_general_flags_match_oracle(api, dtype):
+    n = 6
+    rng = np.random.default_rng(2)
+    a = rng.random((8, n, n)) + np.eye(n)
+    a[1, :, 2] = 0.0                 # zero column: pivot 3 is exactly zero
+    a[4, 3] = a[4, 1]                # duplicate row: exactly singular
+    a[6] = 0.0                       # zero matrix: info 1
+    flat = orc.to_colmajor(a.astype(dtype))
+    got, info = api.general_inverse_host(flat, n)
+    want, oinfo = orc.gauss_jordan_inverse(flat, n)
+    assert info[1] == 3 and info[6] == 1
+    assert info[1] == oinfo[1] and info[6] == oinfo[6]
+    # a duplicated row is singular in exact arithmetic; in floating point the last pivot may be a
+    # rounding residue instead of 0 -- the CUDA path must agree with the oracle either way
+    assert (info[4] != 0) == (oinfo[4] != 0)
+    good = (info == 0) & (oinfo == 0) & (np.arange(8) != 4)
+    assert normwise_err(orc.from_colmajor(got, n)[good], orc.from_colmajor(want, n)[good]) <= TOL[np.dtype(dtype)]
+
+
+# --------------------------------------------------------------------------------------- GP mean / variance
+@pytest.mark.parametrize("n", [8, 16, 32, 64])
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_gp_reference_fixtures(api, fixtures_dir, n, dtype):
+    g = {k: orc.to_colmajor(load_fixture(fixtures_dir, f"gaussian_100_{n}x{n}/{k}.mats", dtype))
+         for k in ("a", "b", "c", "d", "e", "means", "variances")}
+    keep = {k: v.copy() for k, v in g.items()}
+    means, var, info = api.gp_host(n, g["a"], g["b"], g["c"], g["d"], g["e"])
+    assert not info.any()
+    for k in ("a", "b", "c", "d", "e"):                       # inputs are NOT destroyed (gauss_cpu.h:42 is)
+        np.testing.assert_array_equal(g[k], keep[k])
+    om, _ = orc.gp_mean(n, g["a"], g["b"], g["c"], g["d"])
+    ov, _ = orc.gp_variance(n, g["a"], g["b"], g["c"], g["e"])
+    tol = TOL[np.dtype(dtype)]
+    assert np.abs(means - om).max() <= tol * max(1.0, np.abs(om).max())
+    assert np.abs(var - ov).max() <= tol * max(1.0, np.abs(ov).max())
+    assert np.abs(means - g["means"]).max() < 2e-4            # MATLAB goldens, 4 digits
+    assert np.abs(var - g["variances"]).max() < 2e-4
+    # mean-only and variance-only calls give the same numbers as the shared-factor call
+    m2, _, _ = api.gp_host(n, g["a"], g["b"], g["c"], Ds=g["d"])
+    _, v2, _ = api.gp_host(n, g["a"], g["b"], g["c"], Es=g["e"])
+    np.testing.assert_array_equal(m2, means)
+    np.testing.assert_array_equal(v2, var)
+
+
+@pytest.mark.parametrize("n", [1, 3, 13, 33, 100, 128])
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_gp_sizes(api, n, dtype):
+    g = gp_batch(n, 37, dtype, seed=n)
+    flat = {k: orc.to_colmajor(v) if v.ndim == 3 else v.reshape(-1) for k, v in g.items()}
+    means, var, info = api.gp_host(n, flat["a"], flat["b"], flat["c"], flat["d"], flat["e"])
+    assert not info.any()
+    om, _ = orc.gp_mean(n, flat["a"], flat["b"], flat["c"], flat["d"])
+    ov, _ = orc.gp_variance(n, flat["a"], flat["b"], flat["c"], flat["e"])
+    tol = TOL[np.dtype(dtype)]
+    assert np.abs(means - om).max() <= tol
+    assert np.abs(var - ov).max() <= tol
+
+
+def test_gp_128_fixture_vectors_with_synthetic_b(api, fixtures_dir):
+    """gaussian_100_128x128/b.mats is missing from the reference mount: use its a,c,d,e with a
+    generated B (generate_gaussian_matrices.m:20-23) and check against the oracle."""
+    n = 128
+    g = {k: orc.to_colmajor(load_fixture(fixtures_dir, f"gaussian_100_128x128/{k}.mats", np.float32))
+         for k in ("a", "c", "d", "e")}
+    b = orc.to_colmajor(spd_batch(n, 100, np.float32, seed=128))
+    means, var, info = api.gp_host(n, g["a"], b, g["c"], g["d"], g["e"])
+    om, _ = orc.gp_mean(n, g["a"], b, g["c"], g["d"])
+    ov, _ = orc.gp_variance(n, g["a"], b, g["c"], g["e"])
+    assert not info.any()
+    assert np.abs(means - om).max() <= 1e-4 and np.abs(var - ov).max() <= 1e-4
+
+
+def test_gp_flags(api):
+    n = 8
+    g = gp_batch(n, 6, np.float64, seed=9)
+    g["b"][3] = -g["b"][3]
+    flat = {k: orc.to_colmajor(v) if v.ndim == 3 else v.reshape(-1) for k, v in g.items()}
+    means, var, info = api.gp_host(n, flat["a"], flat["b"], flat["c"], flat["d"], flat["e"])
+    _, oinfo = orc.gp_mean(n, flat["a"], flat["b"], flat["c"], flat["d"])
+    np.testing.assert_array_equal(info, oinfo)
+    assert info[3] == 1 and info.sum() == 1
+
+
+# --------------------------------------------------------------------------------------- legacy symbols
+def test_legacy_host_entry_points(api, fixtures_dir):
+    n = 16
+    a = load_fixture(fixtures_dir, "inverse_100_16x16/a.mats", np.float32)
+    flat = orc.to_colmajor(a)
+    want, _ = orc.chol_inverse(flat, n)
+    keep = flat.copy()
+    for fn in (api.inverse_cholesky_batched_gpu, api.inverse_cholesky_mm_batched_gpu,
+               api.inverse_cholesky_mm2_batched_gpu, api.inverse_cholesky_stride_batched_gpu,
+               api.inverse_gauss_batched_gpu, api.inverse_lu_cuda_batched_gpu):
+        got = fn(n, flat)
+        assert normwise_err(orc.from_colmajor(got, n), orc.from_colmajor(want, n)) <= 1e-4
+        np.testing.assert_array_equal(flat, keep)             # As is const (see include/inverse_gpu.h)
+    g = {k: orc.to_colmajor(load_fixture(fixtures_dir, f"gaussian_100_16x16/{k}.mats", np.float32))
+         for k in ("a", "b", "c", "d", "e", "means", "variances")}
+    assert np.abs(api.calcluateMeanGPU(16, g["a"], g["b"], g["c"], g["d"]) - g["means"]).max() < 2e-4
+    assert np.abs(api.calcluateVarianceGPU(16, g["a"], g["b"], g["c"], g["e"]) - g["variances"]).max() < 2e-4
+
+
+@pytest.mark.parametrize("ptrs_on", ["pinned_host", "device"])
+def test_legacy_device_entry_points(api, torch, ptrs_on):
+    """`Array *devAs` flavour: pitched per-matrix device pointers like batchedCudaMalloc
+    (reference src/helper.cu:103-118), pointer array in pinned host memory (as upstream) or on the device."""
+    from cuda_matrix_inversion_b200 import lib
+    n, batch, pitch = 12, 40, 640            # 12*12*4 = 576 bytes, rows padded to 640
+    a = spd_batch(n, batch, np.float32, seed=77)
+    d_a = torch.zeros(batch * pitch // 4, dtype=torch.float32, device="cuda")
+    d_o = torch.zeros_like(d_a)
+    d_a.view(batch, pitch // 4)[:, : n * n] = torch.from_numpy(orc.to_colmajor(a)).view(batch, n * n).cuda()
+    pa = torch.tensor([d_a.data_ptr() + k * pitch for k in range(batch)], dtype=torch.int64)
+    po = torch.tensor([d_o.data_ptr() + k * pitch for k in range(batch)], dtype=torch.int64)
+    if ptrs_on == "pinned_host":
+        pa, po = pa.pin_memory(), po.pin_memory()
+    else:
+        pa, po = pa.cuda(), po.cuda()
+
+    def out():
+        torch.cuda.synchronize()
+        return orc.from_colmajor(d_o.view(batch, pitch // 4)[:, : n * n].contiguous().cpu().numpy().reshape(-1), n)
+
+    want = np.linalg.inv(a.astype(np.float64))
+    for name in ("inverse_cholesky_batched_device", "inverse_cholesky_mm_batched_device",
+                 "inverse_cholesky_mm2_batched_device", "inverse_gauss_batched_device",
+                 "inverse_lu_cuda_batched_device"):
+        d_o.zero_()
+        getattr(lib, name)(None, n, pa.data_ptr(), po.data_ptr(), batch)
+        assert normwise_err(out(), want) <= 1e-4, name
+    # stride family: in place on devAInvs, staged == fused
+    d_o.copy_(d_a)
+    lib.decompose_cholesky_stride_batched_device(None, n, pa.data_ptr(), po.data_ptr(), batch)
+    l = out().astype(np.float64)
+    assert normwise_err(l, np.linalg.cholesky(a.astype(np.float64))) <= 1e-4
+    lib.inverse_upper_stride_batched_device(None, n, pa.data_ptr(), po.data_ptr(), batch)
+    assert normwise_err(out(), np.linalg.inv(np.linalg.cholesky(a.astype(np.float64)))) <= 1e-4
+    lib.multiply_upper_stride_batched_device(None, n, pa.data_ptr(), po.data_ptr(), batch)
+    staged = out().copy()
+    assert normwise_err(staged, want) <= 1e-4
+    d_o.copy_(d_a)
+    lib.inverse_cholesky_stride_batched_device(None, n, pa.data_ptr(), po.data_ptr(), batch)
+    assert normwise_err(out(), want) <= 1e-4
+    # decompose_cholesky_batched_device factors devAs in place
+    d_o.copy_(d_a)
+    lib.decompose_cholesky_batched_device(None, n, po.data_ptr(), pa.data_ptr(), batch)
+    assert normwise_err(out(), np.linalg.cholesky(a.astype(np.float64))) <= 1e-4
+
+
+# --------------------------------------------------------------------------------------- host pipeline
+def test_host_pipeline_chunking_and_pinned_path(api, torch, monkeypatch):
+    """Many chunks, ragged last chunk, pageable and pinned user buffers give identical results."""
+    n, batch = 32, 3001
+    a = spd_batch(n, batch, np.float32, seed=31)
+    flat = orc.to_colmajor(a)
+    base, info0 = api.spd_inverse_host(flat, n)
+    monkeypatch.setenv("INVGPU_CHUNK_MB", "1")
+    small, info1 = api.spd_inverse_host(flat, n)
+    np.testing.assert_array_equal(base, small)
+    pin_in = torch.from_numpy(flat).pin_memory()
+    pin_out = torch.empty_like(pin_in).pin_memory()
+    got, info2 = api.spd_inverse_host(pin_in.numpy(), n, out=pin_out.numpy())
+    np.testing.assert_array_equal(got, base)
+    assert not info0.any() and not info1.any() and not info2.any()
+    want, _ = orc.chol_inverse(flat[: 64 * n * n], n)
+    assert normwise_err(orc.from_colmajor(base[: 64 * n * n], n), orc.from_colmajor(want, n)) <= 1e-4
+
+
+# --------------------------------------------------------------------------------------- full-size properties
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_full_size_1m_32x32_properties(api, torch, dtype):
+    """BASELINE config 3 (2^20 x 32x32): residual on a sample, inverse-of-inverse, scaling law."""
+    n, batch = 32, 1 << 20
+    tdt = torch.float32 if dtype == np.float32 else torch.float64
+    gen = torch.Generator(device="cuda").manual_seed(1234)
+    r = torch.rand((batch, n, n), generator=gen, device="cuda", dtype=tdt)
+    a = r + r.transpose(1, 2) + n * torch.eye(n, device="cuda", dtype=tdt)
+    del r
+    inv = torch.empty_like(a)
+    info = torch.full((batch,), -1, dtype=torch.int32, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    api.spd_inverse_device(a.data_ptr(), inv.data_ptr(), n, batch, dtype, info.data_ptr(), st)
+    torch.cuda.synchronize()
+    assert int(info.abs().max()) == 0
+    tol = TOL[np.dtype(dtype)]
+    idx = torch.randint(0, batch, (4096,), device="cuda")
+    res = (a[idx].double() @ inv[idx].double() - torch.eye(n, device="cuda", dtype=torch.float64)).abs().sum(-1).max()
+    assert float(res) <= tol
+    # oracle on a slice of the very same device-generated inputs
+    sl = a[:256].cpu().numpy()
+    want, _ = orc.chol_inverse(orc.to_colmajor(sl), n)
+    assert normwise_err(inv[:256].cpu().numpy(), orc.from_colmajor(want, n)) <= tol
+    # inverse of the inverse returns A
+    back = torch.empty_like(a)
+    api.spd_inverse_device(inv.data_ptr(), back.data_ptr(), n, batch, dtype, info.data_ptr(), st)
+    torch.cuda.synchronize()
+    assert int(info.abs().max()) == 0
+    rel = ((back - a).abs().amax(dim=(1, 2)) / a.abs().amax(dim=(1, 2))).max()
+    assert float(rel) <= 10 * tol
+    # inv(c A) = inv(A) / c, bit-for-bit for a power of two
+    a.mul_(4.0)
+    api.spd_inverse_device(a.data_ptr(), back.data_ptr(), n, batch, dtype, info.data_ptr(), st)
+    torch.cuda.synchronize()
+    assert torch.equal(back * 4.0, inv)
+
+
+def test_full_size_gp_25k_128(api, torch):
+    """One GPU's shard of BASELINE config 4 (200k x 128x128 over 8 GPUs = 25k per GPU)."""
+    n, batch = 128, 25000
+    gen = torch.Generator(device="cuda").manual_seed(4321)
+    r = torch.rand((batch, n, n), generator=gen, device="cuda")
+    b = r + r.transpose(1, 2) + n * torch.eye(n, device="cuda")
+    del r
+    a, c, d = (torch.rand((batch, n), generator=gen, device="cuda") for _ in range(3))
+    e = torch.rand((batch,), generator=gen, device="cuda")
+    means = torch.empty(batch, device="cuda")
+    var = torch.empty(batch, device="cuda")
+    info = torch.full((batch,), -1, dtype=torch.int32, device="cuda")
+    api.gp_device(n, a.data_ptr(), b.data_ptr(), c.data_ptr(), d.data_ptr(), e.data_ptr(), means.data_ptr(),
+                  var.data_ptr(), batch, np.float32, info.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert int(info.abs().max()) == 0
+    k = 128
+    om, _ = orc.gp_mean(n, a[:k].cpu().numpy(), b[:k].cpu().numpy(), c[:k].cpu().numpy(), d[:k].cpu().numpy())
+    ov, _ = orc.gp_variance(n, a[:k].cpu().numpy(), b[:k].cpu().numpy(), c[:k].cpu().numpy(), e[:k].cpu().numpy())
+    assert np.abs(means[:k].cpu().numpy() - om).max() <= 1e-4
+    assert np.abs(var[:k].cpu().numpy() - ov).max() <= 1e-4
+    # linearity in D: mean(A,B,C,2D) = 2 mean(A,B,C,D), exactly
+    d2 = d * 2
+    m2 = torch.empty_like(means)
+    api.gp_device(n, a.data_ptr(), b.data_ptr(), c.data_ptr(), d2.data_ptr(), 0, m2.data_ptr(), 0, batch, np.float32,
+                  0, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert torch.equal(m2, means * 2)
+    # fp64 cross-check on a sample through torch (an independent implementation)
+    idx = torch.arange(0, batch, 97, device="cuda")
+    mm = b[idx].double() + torch.diag_embed(c[idx].double())
+    x = torch.linalg.solve(mm, d[idx].double().unsqueeze(-1)).squeeze(-1)
+    ref = (a[idx].double() * x).sum(-1)
+    assert float((means[idx].double() - ref).abs().max()) <= 1e-4

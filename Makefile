@@ -11,21 +11,23 @@ NVFLAGS  := -O3 -std=c++17 $(ARCH) -lineinfo -Xcompiler -fPIC -Xptxas -v $(EXTRA
 CSRC     := cuda_matrix_inversion_b200/csrc
 LIBDIR   := cuda_matrix_inversion_b200/lib
 LIB      := $(LIBDIR)/libinvgpu.so
-HDRS     := $(wildcard $(CSRC)/*.cuh) $(wildcard include/*.h)
+HDRS     := $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.h) $(wildcard include/*.h)
 
 all: lib cli
 
 lib: $(LIB)
 
-$(LIBDIR)/capi.o: $(CSRC)/capi.cu $(HDRS)
+CUOBJS   := $(LIBDIR)/capi.o $(patsubst $(CSRC)/%.cu,$(LIBDIR)/%.o,$(wildcard $(CSRC)/inst_*.cu))
+
+$(LIBDIR)/%.o: $(CSRC)/%.cu $(HDRS)
 	@mkdir -p $(LIBDIR)
-	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(LIBDIR)/ptxas_capi.log || (cat $(LIBDIR)/ptxas_capi.log; false)
+	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(LIBDIR)/ptxas_$*.log || (cat $(LIBDIR)/ptxas_$*.log; false)
 
 $(LIBDIR)/mats_io.o: $(CSRC)/mats_io.c include/helper_cpu.h include/types.h
 	@mkdir -p $(LIBDIR)
 	$(CC) -O2 -fPIC -std=gnu11 -c $< -o $@
 
-$(LIB): $(LIBDIR)/capi.o $(LIBDIR)/mats_io.o
+$(LIB): $(CUOBJS) $(LIBDIR)/mats_io.o
 	$(NVCC) $(ARCH) -shared -o $@ $^ -cudart static
 
 cli: bin/inverse_bench bin/gauss_bench

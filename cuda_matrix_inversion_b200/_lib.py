@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libinvgpu.so")
+LIB_PATH = os.environ.get("INVGPU_LIB", os.path.join(_HERE, "lib", "libinvgpu.so"))   # override: kernel-variant experiments
 
 _i64 = C.c_longlong
 _vp = C.c_void_p

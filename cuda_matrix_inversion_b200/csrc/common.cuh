@@ -53,6 +53,10 @@ template <typename T> __device__ __forceinline__ T dev_abs(T x);
 template <> __device__ __forceinline__ float dev_abs<float>(float x) { return fabsf(x); }
 template <> __device__ __forceinline__ double dev_abs<double>(double x) { return fabs(x); }
 
+template <typename T> __device__ __forceinline__ T dev_nan();
+template <> __device__ __forceinline__ float dev_nan<float>() { return __int_as_float(0x7fc00000); }
+template <> __device__ __forceinline__ double dev_nan<double>() { return __longlong_as_double(0x7ff8000000000000LL); }
+
 // Group = the threads that cooperate on one matrix: a warp (G == 32) or the whole CTA.
 template <int G>
 struct Group {

@@ -37,6 +37,9 @@ struct DeviceState {
     cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
     cudaEvent_t ev_in[kSlots], ev_comp[kSlots], ev_out[kSlots];
     bool streams_ready = false;
+    // scratch of the fused GP tile kernels (natural-order info recomputation of flagged matrices)
+    void *gp_scratch = nullptr;
+    size_t gp_scratch_bytes = 0;
 };
 
 DeviceState *device_state(int *err);   // state of the calling thread's current device

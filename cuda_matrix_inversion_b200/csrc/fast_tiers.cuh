@@ -1,23 +1,79 @@
-// fast_tiers.cuh -- dispatch into the register-tiled tiers (warp tier n <= 32, CTA tier
-// n in {64,128}); returns INVGPU_NO_FAST_PATH when a shape has no specialised kernel, in which
+// fast_tiers.cuh -- dispatch into the register-tiled tiers (tile_kernels.cuh, instantiated in the
+// inst_*.cu units); returns INVGPU_NO_FAST_PATH when a shape has no specialised kernel, in which
 // case the any-n shared-memory kernels of generic_smem.cuh serve it.
 #pragma once
 
+#include <type_traits>
+
 #include "engine.cuh"
+#include "generic_smem.cuh"
+#include "tile_configs.h"
+#include "tile_launch.cuh"
 
 #define INVGPU_NO_FAST_PATH (-1000)
 
 namespace invgpu {
 
+template <typename T>
+static bool dense_aligned(const StridedIO<T> &io, int n) {
+    return ((uintptr_t)io.in % 16 == 0) && ((uintptr_t)io.out % 16 == 0) &&
+           (io.in_stride * (i64)sizeof(T)) % 16 == 0 && (io.out_stride * (i64)sizeof(T)) % 16 == 0 &&
+           io.in_stride >= (i64)n * n && io.out_stride >= (i64)n * n;
+}
+
+// one `if` per instantiated configuration, generated from the X-macro lists
+#define INVGPU_TILE_TRY(TT, N, TR, TC, PERM, STAGES_, MINB)                                         \
+    if (std::is_same<T, TT>::value && n == N && STAGES == STAGES_)                                   \
+        return launch_tile_spd<TT, N, TR, TC, PERM, STAGES_, MINB>(                                  \
+            *reinterpret_cast<StridedIO<TT> *>(&io), batch, dInfo, st, ds);
+
+template <typename T, int STAGES>
+static int fast_spd_dense(StridedIO<T> io, int n, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds) {
+    if (!dense_aligned(io, n)) return INVGPU_NO_FAST_PATH;
+    INVGPU_TILE_SPD_ALL(INVGPU_TILE_TRY)
+    return INVGPU_NO_FAST_PATH;
+}
+
 template <typename T, typename IO, int STAGES>
-static int fast_spd(IO, int, i64, int *, cudaStream_t, DeviceState *) { return INVGPU_NO_FAST_PATH; }
+struct FastSpd {   // pointer-array batches: per-matrix alignment is unknown on the host -> generic tier
+    static int run(IO, int, i64, int *, cudaStream_t, DeviceState *) { return INVGPU_NO_FAST_PATH; }
+};
+template <typename T, int STAGES>
+struct FastSpd<T, StridedIO<T>, STAGES> {
+    static int run(StridedIO<T> io, int n, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds) {
+        return fast_spd_dense<T, STAGES>(io, n, batch, dInfo, st, ds);
+    }
+};
+
+template <typename T, typename IO, int STAGES>
+static int fast_spd(IO io, int n, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds) {
+    return FastSpd<T, IO, STAGES>::run(io, n, batch, dInfo, st, ds);
+}
 
 template <typename T, typename IO>
 static int fast_general(IO, int, i64, int *, cudaStream_t, DeviceState *) { return INVGPU_NO_FAST_PATH; }
 
-template <typename T>
-static int fast_gp(GpIO<T>, int, i64, int *, cudaStream_t, DeviceState *) { return INVGPU_NO_FAST_PATH; }
+#define INVGPU_TILE_TRY_GP(TT, N, TR, TC, MINB)                                                     \
+    if (std::is_same<T, TT>::value && n == N)                                                        \
+        return launch_tile_gp<TT, N, TR, TC, MINB>(*reinterpret_cast<GpIO<TT> *>(&io), batch, dInfo, st, ds);
 
-static const char *fast_tier_name(int, int, int) { return "generic"; }
+template <typename T>
+static int fast_gp(GpIO<T> io, int n, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds) {
+    const uintptr_t all = (uintptr_t)io.a | (uintptr_t)io.b | (uintptr_t)io.c | (uintptr_t)io.d;
+    if (all % 16 != 0 || ((size_t)n * sizeof(T)) % 16 != 0) return INVGPU_NO_FAST_PATH;
+    INVGPU_TILE_GP_ALL(INVGPU_TILE_TRY_GP)
+    return INVGPU_NO_FAST_PATH;
+}
+
+// op: 0 = spd inverse, 1 = general inverse, 2 = gp; which tier serves a dense aligned batch
+#define INVGPU_TILE_NAME(TT, N, TR, TC, PERM, STAGES_, MINB) \
+    if (op == 0 && n == N && dtype_bytes == (int)sizeof(TT) && STAGES_ == 7) return TR * TC <= 32 ? "warp-tile" : "cta-tile";
+#define INVGPU_TILE_NAME_GP(TT, N, TR, TC, MINB) \
+    if (op == 2 && n == N && dtype_bytes == (int)sizeof(TT)) return TR * TC <= 32 ? "warp-tile" : "cta-tile";
+static const char *fast_tier_name(int op, int n, int dtype_bytes) {
+    INVGPU_TILE_SPD_ALL(INVGPU_TILE_NAME)
+    INVGPU_TILE_GP_ALL(INVGPU_TILE_NAME_GP)
+    return "generic";
+}
 
 }  // namespace invgpu

@@ -130,6 +130,13 @@ __device__ __forceinline__ void group_argmax(T &best, int &idx, T *sval, int *si
     }
 }
 
+// A flagged matrix gets a deterministic output: every element NaN (LAPACK leaves a half-finished
+// factor there; a NaN cannot be mistaken for a result).
+template <typename T, int G>
+__device__ __forceinline__ void fill_nan(T *dst, int count, int t) {
+    for (int idx = t; idx < count; idx += G) dst[idx] = dev_nan<T>();
+}
+
 // ---------------------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------------------
@@ -165,7 +172,7 @@ spd_generic_kernel(IO io, int n, i64 batch, int *__restrict__ info) {
         int st = 0;
         if (STAGES & SPD_POTRF) st = potrf_packed<T, G>(S, n, n, t);
         if (t == 0 && info) info[m] = st;
-        if (st) continue;
+        if (st) { fill_nan<T, G>(dst, nn, t); continue; }
         if (STAGES & SPD_TRTRI) trtri_packed<T, G>(S, n, t);
         if (STAGES & SPD_LAUUM) lauum_packed<T, G>(S, n, t);
         for (int idx = t; idx < nn; idx += G) {      // coalesced store
@@ -237,7 +244,7 @@ gj_generic_kernel(IO io, int n, i64 batch, int *__restrict__ info) {
             Group<G>::sync();
         }
         if (t == 0 && info) info[m] = st;
-        if (st) continue;
+        if (st) { fill_nan<T, G>(dst, nn, t); continue; }
         for (int i = t; i < n; i += G) {                       // undo interchanges as column swaps, own row only
             T *ri = S + i * ld;
             for (int k = n - 1; k >= 0; --k) {
@@ -282,7 +289,13 @@ gp_generic_kernel(GpIO<T> io, int n, i64 batch, int *__restrict__ info) {
         Group<G>::sync();
         const int st = potrf_packed<T, G>(S, n, n + 2, t);
         if (t == 0 && info) info[m] = st;
-        if (st) continue;
+        if (st) {
+            if (t == 0) {
+                if (io.means) io.means[m] = dev_nan<T>();
+                if (io.variances) io.variances[m] = dev_nan<T>();
+            }
+            continue;
+        }
         T pm = 0, pq = 0;
         for (int j = t; j < n; j += G) { const T x = ra[j]; pm = fma(x, rd[j], pm); pq = fma(x, x, pq); }
         pm = group_sum<T, G>(pm, scratch, t);

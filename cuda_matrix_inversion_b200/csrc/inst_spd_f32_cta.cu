@@ -1,0 +1,4 @@
+#define INVGPU_TILE_DEFINE
+#include "tile_launch.cuh"
+#include "tile_configs.h"
+INVGPU_TILE_SPD_F32_INV_CTA(INVGPU_TILE_INSTANTIATE)

@@ -1,0 +1,43 @@
+// tile_configs.h -- the register-tiled kernels that are instantiated (one translation unit per
+// group, compiled in parallel), as X-macro lists.
+//   SPD : X(T, N, TR, TC, PERM, STAGES, MINB)     GP : X(T, N, TR, TC, MINB)
+//   TR x TC = thread grid per matrix, MINB = resident CTAs per SM the register allocator must allow
+#pragma once
+
+#ifndef INVGPU_F32_N32_MINB
+#define INVGPU_F32_N32_MINB 3
+#endif
+
+// fp32 SPD inverse, warp tiers
+#define INVGPU_TILE_SPD_F32_INV(X)                              \
+    X(float, 8, 1, 1, true, 7, 4)                               \
+    X(float, 16, 2, 2, true, 7, 4)                              \
+    X(float, 32, 4, 2, true, 7, INVGPU_F32_N32_MINB)            \
+    X(float, 64, 8, 4, true, 7, 3)
+// fp32 SPD inverse, CTA tier
+#define INVGPU_TILE_SPD_F32_INV_CTA(X)                          \
+    X(float, 128, 16, 16, true, 7, 2)
+
+// fp64 SPD inverse
+#define INVGPU_TILE_SPD_F64_INV(X)                              \
+    X(double, 8, 1, 1, true, 7, 2)                              \
+    X(double, 16, 2, 2, true, 7, 2)                             \
+    X(double, 32, 4, 4, true, 7, 2)                             \
+    X(double, 64, 8, 8, true, 7, 4)
+#define INVGPU_TILE_SPD_F64_INV_CTA(X)                          \
+    X(double, 128, 16, 16, true, 7, 1)
+
+// fused GP mean / variance
+#define INVGPU_TILE_GP_F32(X)                                   \
+    X(float, 32, 4, 2, 3)                                       \
+    X(float, 64, 8, 4, 3)                                       \
+    X(float, 128, 16, 16, 2)
+#define INVGPU_TILE_GP_F64(X)                                   \
+    X(double, 32, 4, 4, 2)                                      \
+    X(double, 64, 8, 8, 4)                                      \
+    X(double, 128, 16, 16, 1)
+
+#define INVGPU_TILE_SPD_ALL(X)                                  \
+    INVGPU_TILE_SPD_F32_INV(X) INVGPU_TILE_SPD_F32_INV_CTA(X)   \
+    INVGPU_TILE_SPD_F64_INV(X) INVGPU_TILE_SPD_F64_INV_CTA(X)
+#define INVGPU_TILE_GP_ALL(X) INVGPU_TILE_GP_F32(X) INVGPU_TILE_GP_F64(X)

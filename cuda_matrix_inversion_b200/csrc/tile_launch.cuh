@@ -1,0 +1,67 @@
+// tile_launch.cuh -- host launchers of the register-tiled kernels.  Declared everywhere, defined
+// (and explicitly instantiated) only in the inst_*.cu translation units.
+#pragma once
+
+#include "engine.cuh"
+#include "generic_smem.cuh"   // SPD_* stage bits
+
+namespace invgpu {
+
+template <typename T, int N, int TR, int TC, bool PERM, int STAGES, int MINB>
+int launch_tile_spd(StridedIO<T> io, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds);
+
+template <typename T, int N, int TR, int TC, int MINB>
+int launch_tile_gp(GpIO<T> io, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds);
+
+}  // namespace invgpu
+
+#ifdef INVGPU_TILE_DEFINE
+#include "tile_kernels.cuh"
+
+namespace invgpu {
+
+template <typename T, int N, int TR, int TC, bool PERM, int STAGES, int MINB>
+int launch_tile_spd(StridedIO<T> io, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds) {
+    using G = TileGeo<N, TR, TC, PERM>;
+    auto kern = tile_spd_kernel<T, N, TR, TC, PERM, StridedIO<T>, STAGES, MINB>;
+    const size_t smem = (size_t)G::MPB * G::SMEM_WORDS * sizeof(T);
+    int grid = 0;
+    int rc = persistent_grid(kern, G::BLOCK, smem, (batch + G::MPB - 1) / G::MPB, ds, &grid);
+    if (rc) return rc;
+    kern<<<grid, G::BLOCK, smem, st>>>(io, batch, dInfo);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return (int)cudaGetLastError();
+}
+
+template <typename T, int N, int TR, int TC, int MINB>
+int launch_tile_gp(GpIO<T> io, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds) {
+    using G = TileGeo<N, TR, TC, true>;
+    auto kern = tile_gp_kernel<T, N, TR, TC, MINB>;
+    constexpr int WORDS = 2 * (N + 4) + (G::LANES < 32 ? 8 : 0) + ((2 * (N + 4)) % 32 == 0 ? 0 : 32 - (2 * (N + 4)) % 32);
+    const size_t smem = (size_t)G::MPB * WORDS * sizeof(T);
+    int grid = 0;
+    int rc = persistent_grid(kern, G::BLOCK, smem, (batch + G::MPB - 1) / G::MPB, ds, &grid);
+    if (rc) return rc;
+    // scratch for the (rare) natural-order info recomputation of flagged matrices
+    const size_t need = (size_t)grid * G::MPB * N * N * sizeof(T);
+    if (ds->gp_scratch_bytes < need) {
+        std::lock_guard<std::mutex> lk(engine_mutex());
+        if (ds->gp_scratch_bytes < need) {
+            if (ds->gp_scratch) cudaFree(ds->gp_scratch);
+            ds->gp_scratch = nullptr; ds->gp_scratch_bytes = 0;
+            INVGPU_TRY(cudaMalloc(&ds->gp_scratch, need));
+            ds->gp_scratch_bytes = need;
+        }
+    }
+    kern<<<grid, G::BLOCK, smem, st>>>(io, batch, dInfo, (T *)ds->gp_scratch);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace invgpu
+
+#define INVGPU_TILE_INSTANTIATE(T, N, TR, TC, PERM, STAGES, MINB) \
+    template int invgpu::launch_tile_spd<T, N, TR, TC, PERM, STAGES, MINB>(invgpu::StridedIO<T>, invgpu::i64, int *, cudaStream_t, invgpu::DeviceState *);
+#define INVGPU_TILE_INSTANTIATE_GP(T, N, TR, TC, MINB) \
+    template int invgpu::launch_tile_gp<T, N, TR, TC, MINB>(invgpu::GpIO<T>, invgpu::i64, int *, cudaStream_t, invgpu::DeviceState *);
+#endif

@@ -12,7 +12,7 @@
  *     NULL = legacy default stream) and never synchronise.
  *   - info (may be NULL): one int per matrix, LAPACK semantics.  SPD paths: spotrf info
  *     (k > 0: leading minor of order k is not positive definite).  General path: sgetrf info
- *     (k > 0: pivot k is exactly zero).  A flagged matrix's output is left unwritten; the
+ *     (k > 0: pivot k is exactly zero).  A flagged matrix's output is filled with NaN; the
  *     rest of the batch is processed normally (the reference aborts the process instead,
  *     src/inverse.c:94, src/gauss/inverse_gpu.cu:36).
  *   - return value: 0 on success, a positive cudaError_t, or a negative INVGPU_E* code.

@@ -116,8 +116,8 @@ def test_spd_flags_match_oracle(api, fixtures_dir, dtype):
     good = info == 0
     tol = TOL[np.dtype(dtype)]
     assert normwise_err(orc.from_colmajor(got, n)[good], orc.from_colmajor(want, n)[good]) <= tol
-    # flagged matrices are left unwritten, the rest of the batch is processed
-    assert (orc.from_colmajor(got, n)[~good] == 777.0).all()
+    # flagged matrices come back as NaN, the rest of the batch is processed
+    assert np.isnan(orc.from_colmajor(got, n)[~good]).all()
     # the reference's own singular fixture (simpleMean/b.mats, all 1.1)
     b = load_fixture(fixtures_dir, "simpleMean/b.mats", dtype)
     _, info = api.spd_inverse_host(orc.to_colmajor(b), 2)
@@ -180,9 +180,11 @@ def test_general_inverse_square_100_64_64_regenerated(api, golden_dir):
     err = np.abs(got3 - inv64).reshape(100, -1).max(1) / np.abs(inv64).reshape(100, -1).max(1)
     assert (err <= np.maximum(1e-4, 16 * np.finfo(np.float32).eps * cond)).all()
     want, _ = orc.gauss_jordan_inverse(flat, 64)
-    ok = cond < 500
-    assert ok.sum() > 10
-    assert normwise_err(got3[ok], orc.from_colmajor(want, 64)[ok]) <= 1e-4
+    want3 = orc.from_colmajor(want, 64)
+    dev = np.abs(got3 - want3).reshape(100, -1).max(1) / np.abs(want3).reshape(100, -1).max(1)
+    assert (dev <= np.maximum(1e-4, 16 * np.finfo(np.float32).eps * cond)).all()   # cond of U(0,1) 64x64: 1e2..1e4
+    res = np.abs(a.astype(np.float64) @ got3.astype(np.float64) - np.eye(64)).sum(-1).max(-1)
+    assert (res <= np.maximum(1e-4, 64 * np.finfo(np.float32).eps * cond)).all()
 
 
 @pytest.mark.parametrize("n", [1, 2, 3, 7, 13, 31, 33, 50, 100])

@@ -32,9 +32,9 @@ $(LIB): $(CUOBJS) $(LIBDIR)/mats_io.o
 
 cli: bin/inverse_bench bin/gauss_bench
 
-bin/%: $(CSRC)/%.c $(LIB) $(HDRS)
+bin/%: $(CSRC)/%.c $(CSRC)/bench_common.h $(LIB) $(HDRS)
 	@mkdir -p bin
-	$(CC) -O2 -std=gnu11 -fopenmp -Iinclude -o $@ $< -L$(LIBDIR) -linvgpu -Wl,-rpath,'$$ORIGIN/../$(LIBDIR)' -lm
+	$(CC) -O2 -std=gnu11 -fopenmp -o $@ $< -L$(LIBDIR) -linvgpu -Wl,-rpath,'$$ORIGIN/../$(LIBDIR)' -ldl -lm
 
 oracle:
 	$(MAKE) -C oracle

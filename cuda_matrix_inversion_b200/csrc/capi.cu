@@ -338,6 +338,8 @@ int invgpu_device_count(void) {
     return n;
 }
 
+int invgpu_set_device(int device) { return (int)cudaSetDevice(device); }
+
 const char *invgpu_error_string(int code) {
     if (code == 0) return "success";
     if (code == INVGPU_EARG) return "invalid argument";

@@ -40,6 +40,7 @@ typedef long long invgpu_i64;
 /* ---- library / device ------------------------------------------------------------------ */
 const char *invgpu_version(void);
 int invgpu_device_count(void);                 /* 0 when no CUDA device is usable */
+int invgpu_set_device(int device);             /* cudaSetDevice for the calling host thread (multi-GPU sharding) */
 const char *invgpu_error_string(int code);
 /* number of kernels launched by this library on the calling thread's device since load
  * (used by bench.py's `gpu_launches`). */

@@ -50,8 +50,21 @@ static int fast_spd(IO io, int n, i64 batch, int *dInfo, cudaStream_t st, Device
     return FastSpd<T, IO, STAGES>::run(io, n, batch, dInfo, st, ds);
 }
 
+// smallest instantiated padded order >= n wins (the lists are ascending in N)
+#define INVGPU_GJ_TRY(TT, N, ROWS, MINB)                                                            \
+    if (std::is_same<T, TT>::value && n <= N)                                                        \
+        return launch_gj<TT, N, ROWS, typename IOCast<IO, TT>::type, MINB>(                          \
+            *reinterpret_cast<typename IOCast<IO, TT>::type *>(&io), n, batch, dInfo, st, ds);
+
+template <typename IO, typename TT> struct IOCast;
+template <typename T, typename TT> struct IOCast<StridedIO<T>, TT> { typedef StridedIO<TT> type; };
+template <typename T, typename TT> struct IOCast<PtrIO<T>, TT> { typedef PtrIO<TT> type; };
+
 template <typename T, typename IO>
-static int fast_general(IO, int, i64, int *, cudaStream_t, DeviceState *) { return INVGPU_NO_FAST_PATH; }
+static int fast_general(IO io, int n, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds) {
+    INVGPU_GJ_ALL(INVGPU_GJ_TRY)
+    return INVGPU_NO_FAST_PATH;
+}
 
 #define INVGPU_TILE_TRY_GP(TT, N, TR, TC, MINB)                                                     \
     if (std::is_same<T, TT>::value && n == N)                                                        \
@@ -70,7 +83,10 @@ static int fast_gp(GpIO<T> io, int n, i64 batch, int *dInfo, cudaStream_t st, De
     if (op == 0 && n == N && dtype_bytes == (int)sizeof(TT) && STAGES_ == 7) return TR * TC <= 32 ? "warp-tile" : "cta-tile";
 #define INVGPU_TILE_NAME_GP(TT, N, TR, TC, MINB) \
     if (op == 2 && n == N && dtype_bytes == (int)sizeof(TT)) return TR * TC <= 32 ? "warp-tile" : "cta-tile";
+#define INVGPU_GJ_NAME(TT, N, ROWS, MINB) \
+    if (op == 1 && n <= N && dtype_bytes == (int)sizeof(TT)) return "warp-rowlane";
 static const char *fast_tier_name(int op, int n, int dtype_bytes) {
+    INVGPU_GJ_ALL(INVGPU_GJ_NAME)
     INVGPU_TILE_SPD_ALL(INVGPU_TILE_NAME)
     INVGPU_TILE_GP_ALL(INVGPU_TILE_NAME_GP)
     return "generic";

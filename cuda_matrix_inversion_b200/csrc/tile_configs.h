@@ -41,3 +41,8 @@
     INVGPU_TILE_SPD_F32_INV(X) INVGPU_TILE_SPD_F32_INV_CTA(X)   \
     INVGPU_TILE_SPD_F64_INV(X) INVGPU_TILE_SPD_F64_INV_CTA(X)
 #define INVGPU_TILE_GP_ALL(X) INVGPU_TILE_GP_F32(X) INVGPU_TILE_GP_F64(X)
+
+// general inverse, lane = row Gauss-Jordan (gj_kernels.cuh):  X(T, N, ROWS, MINB); N = padded order
+#define INVGPU_GJ_F32(X) X(float, 8, 1, 4) X(float, 16, 1, 4) X(float, 32, 1, 4)
+#define INVGPU_GJ_F64(X) X(double, 8, 1, 4) X(double, 16, 1, 4) X(double, 32, 1, 3)
+#define INVGPU_GJ_ALL(X) INVGPU_GJ_F32(X) INVGPU_GJ_F64(X)

@@ -13,12 +13,29 @@ int launch_tile_spd(StridedIO<T> io, i64 batch, int *dInfo, cudaStream_t st, Dev
 template <typename T, int N, int TR, int TC, int MINB>
 int launch_tile_gp(GpIO<T> io, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds);
 
+template <typename T, int N, int ROWS, typename IO, int MINB>
+int launch_gj(IO io, int n, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds);
+
 }  // namespace invgpu
 
 #ifdef INVGPU_TILE_DEFINE
 #include "tile_kernels.cuh"
+#include "gj_kernels.cuh"
 
 namespace invgpu {
+
+template <typename T, int N, int ROWS, typename IO, int MINB>
+int launch_gj(IO io, int n, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds) {
+    using G = GjGeo<T, N, ROWS>;
+    auto kern = gj_rowlane_kernel<T, N, ROWS, IO, MINB>;
+    const size_t smem = (size_t)G::MPB * G::WORDS * sizeof(T);
+    int grid = 0;
+    int rc = persistent_grid(kern, G::BLOCK, smem, (batch + G::MPB - 1) / G::MPB, ds, &grid);
+    if (rc) return rc;
+    kern<<<grid, G::BLOCK, smem, st>>>(io, n, batch, dInfo);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return (int)cudaGetLastError();
+}
 
 template <typename T, int N, int TR, int TC, bool PERM, int STAGES, int MINB>
 int launch_tile_spd(StridedIO<T> io, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds) {
@@ -45,7 +62,8 @@ int launch_tile_gp(GpIO<T> io, i64 batch, int *dInfo, cudaStream_t st, DeviceSta
     // scratch for the (rare) natural-order info recomputation of flagged matrices
     const size_t need = (size_t)grid * G::MPB * N * N * sizeof(T);
     if (ds->gp_scratch_bytes < need) {
-        std::lock_guard<std::mutex> lk(engine_mutex());
+        static std::mutex scratch_mutex;              // not engine_mutex(): the host pipeline holds that one
+        std::lock_guard<std::mutex> lk(scratch_mutex);
         if (ds->gp_scratch_bytes < need) {
             if (ds->gp_scratch) cudaFree(ds->gp_scratch);
             ds->gp_scratch = nullptr; ds->gp_scratch_bytes = 0;
@@ -62,6 +80,9 @@ int launch_tile_gp(GpIO<T> io, i64 batch, int *dInfo, cudaStream_t st, DeviceSta
 
 #define INVGPU_TILE_INSTANTIATE(T, N, TR, TC, PERM, STAGES, MINB) \
     template int invgpu::launch_tile_spd<T, N, TR, TC, PERM, STAGES, MINB>(invgpu::StridedIO<T>, invgpu::i64, int *, cudaStream_t, invgpu::DeviceState *);
+#define INVGPU_GJ_INSTANTIATE(T, N, ROWS, MINB) \
+    template int invgpu::launch_gj<T, N, ROWS, invgpu::StridedIO<T>, MINB>(invgpu::StridedIO<T>, int, invgpu::i64, int *, cudaStream_t, invgpu::DeviceState *); \
+    template int invgpu::launch_gj<T, N, ROWS, invgpu::PtrIO<T>, MINB>(invgpu::PtrIO<T>, int, invgpu::i64, int *, cudaStream_t, invgpu::DeviceState *);
 #define INVGPU_TILE_INSTANTIATE_GP(T, N, TR, TC, MINB) \
     template int invgpu::launch_tile_gp<T, N, TR, TC, MINB>(invgpu::GpIO<T>, invgpu::i64, int *, cudaStream_t, invgpu::DeviceState *);
 #endif

@@ -219,9 +219,13 @@ def test_general_flags_match_oracle(api, dtype):
     want, oinfo = orc.gauss_jordan_inverse(flat, n)
     assert info[1] == 3 and info[6] == 1
     assert info[1] == oinfo[1] and info[6] == oinfo[6]
-    # a duplicated row is singular in exact arithmetic; in floating point the last pivot may be a
-    # rounding residue instead of 0 -- the CUDA path must agree with the oracle either way
-    assert (info[4] != 0) == (oinfo[4] != 0)
+    # A duplicated row is singular in exact arithmetic only: in floating point the last pivot is either
+    # exactly 0 (flag) or a rounding residue (then the "inverse" is astronomically large).  Which of the
+    # two happens depends on fused vs. unfused multiply-add (nvcc contracts a - f*p into one FFMA, in
+    # this engine as in the reference's own kernel src/gauss/batched_invert.cu:75-80; the C oracle
+    # rounds twice), so only the dichotomy itself can be asserted, for both.
+    for flag, res in ((info[4], orc.from_colmajor(got, n)[4]), (oinfo[4], orc.from_colmajor(want, n)[4])):
+        assert flag != 0 or np.abs(res).max() > 1e5
     good = (info == 0) & (oinfo == 0) & (np.arange(8) != 4)
     assert normwise_err(orc.from_colmajor(got, n)[good], orc.from_colmajor(want, n)[good]) <= TOL[np.dtype(dtype)]
 

@@ -39,6 +39,7 @@ def _load() -> C.CDLL:
         sig[f"invgpu_general_inverse_{sfx}"] = (_int, [_vp, _vp, _int, _i64, _vp, _vp])
         sig[f"invgpu_spd_stages_ptrs_{sfx}"] = (_int, [_vp, _vp, _int, _int, _int, _vp, _vp])
         sig[f"invgpu_general_inverse_ptrs_{sfx}"] = (_int, [_vp, _vp, _int, _int, _vp, _vp])
+        sig[f"invgpu_mixed_spd_inverse_{sfx}"] = (_int, [_vp, _vp, _vp, _i64, _vp, _vp])
         sig[f"invgpu_gp_{sfx}"] = (_int, [_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp])
         sig[f"invgpu_spd_inverse_host_{sfx}"] = (_int, [_vp, _vp, _int, _i64, _vp])
         sig[f"invgpu_general_inverse_host_{sfx}"] = (_int, [_vp, _vp, _int, _i64, _vp])

@@ -172,6 +172,17 @@ def general_inverse_ptrs_device(d_ptrs_in: int, d_ptrs_out: int, n: int, batch: 
     _check(fn(d_ptrs_in, d_ptrs_out, n, batch, d_info or None, stream or None), "general_inverse_ptrs_device")
 
 
+def mixed_spd_inverse_device(ptrs_in: np.ndarray, ptrs_out: np.ndarray, ns: np.ndarray, dtype, d_info: int = 0,
+                             stream: int = 0) -> None:
+    """Persistent-CTA scheduler over mixed dimensions: host arrays of device addresses and orders."""
+    ptrs_in = np.ascontiguousarray(ptrs_in, dtype=np.uint64)
+    ptrs_out = np.ascontiguousarray(ptrs_out, dtype=np.uint64)
+    ns = np.ascontiguousarray(ns, dtype=np.int32)
+    fn = getattr(lib, "invgpu_mixed_spd_inverse_" + _sfx(dtype))
+    _check(fn(_np_ptr(ptrs_in), _np_ptr(ptrs_out), _np_ptr(ns), ns.size, d_info or None, stream or None),
+           "mixed_spd_inverse_device")
+
+
 # ----------------------------------------------------------------------------- .mats I/O through the C library
 def read_mats_file(path: str) -> np.ndarray:
     """readMatricesFile (include/helper_cpu.h) -> flat column-major float32 buffer plus shape."""

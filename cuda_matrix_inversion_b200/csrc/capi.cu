@@ -6,6 +6,8 @@
 #include "engine.cuh"
 #include "generic_smem.cuh"
 #include "fast_tiers.cuh"
+#include "mixed_kernels.cuh"
+#include <algorithm>
 
 #include "../../include/invgpu.h"
 #include "../../include/inverse_gpu.h"
@@ -306,6 +308,89 @@ static int host_gp(int n, const T *As, const T *Bs, const T *Cs, const T *Ds, co
     });
 }
 
+// ------------------------------------------------------------------------------------------
+// mixed dimensions: three bucket work lists (<= 32, <= 128, <= 256), each drained by a
+// persistent grid with an atomic ticket; the three kernels run concurrently.
+// ------------------------------------------------------------------------------------------
+template <typename T, int G>
+static int launch_mixed_bucket(const MixedItem *dItems, i64 count, int nmax, int *dInfo, unsigned long long *dTicket,
+                               cudaStream_t st, DeviceState *ds) {
+    if (count == 0) return 0;
+    auto kern = mixed_spd_kernel<T, G>;
+    const int block = G <= 32 ? 256 : G;
+    const int per_unit = G <= 32 ? 8 : 1;
+    const size_t smem = (size_t)per_unit * packed_row(nmax) * sizeof(T);
+    int grid = 0;
+    int rc = persistent_grid(kern, block, smem, (count + per_unit - 1) / per_unit, ds, &grid);
+    if (rc == -2) return INVGPU_EUNSUPPORTED;
+    if (rc) return rc;
+    kern<<<grid, block, smem, st>>>(dItems, count, nmax, dInfo, dTicket);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return (int)cudaGetLastError();
+}
+
+template <typename T>
+static int run_mixed_spd(T *const *hIn, T *const *hOut, const int *hN, i64 count, int *dInfo, cudaStream_t st) {
+    if (!hIn || !hOut || !hN || count < 0) return INVGPU_EARG;
+    if (count == 0) return 0;
+    int err = 0;
+    DeviceState *ds = device_state(&err);
+    if (!ds) return err;
+    std::vector<MixedItem> bucket[3];
+    int nmax[3] = {1, 1, 1};
+    for (i64 i = 0; i < count; ++i) {
+        const int n = hN[i];
+        if (n < 1) return INVGPU_EARG;
+        if (n > 256) return INVGPU_EUNSUPPORTED;
+        const int b = n <= 32 ? 0 : (n <= 128 ? 1 : 2);
+        MixedItem it; it.in = hIn[i]; it.out = hOut[i]; it.n = n; it.index = (int)i;
+        bucket[b].push_back(it);
+        if (n > nmax[b]) nmax[b] = n;
+    }
+    for (int b = 0; b < 3; ++b)                               // longest work first
+        std::stable_sort(bucket[b].begin(), bucket[b].end(), [](const MixedItem &x, const MixedItem &y) { return x.n > y.n; });
+
+    std::lock_guard<std::mutex> lk(engine_mutex());
+    int rc = ensure_pipeline(ds, 0);                          // streams + events
+    if (rc) return rc;
+    const size_t need = (size_t)count * sizeof(MixedItem) + 64;
+    if (ds->mixed_bytes < need) {
+        if (ds->d_mixed) cudaFree(ds->d_mixed);
+        if (ds->h_mixed) cudaFreeHost(ds->h_mixed);
+        ds->d_mixed = nullptr; ds->h_mixed = nullptr; ds->mixed_bytes = 0;
+        INVGPU_TRY(cudaMalloc(&ds->d_mixed, need));
+        INVGPU_TRY(cudaHostAlloc(&ds->h_mixed, need, cudaHostAllocDefault));
+        ds->mixed_bytes = need;
+    }
+    // the staging buffer is reused: wait for the previous call's upload
+    INVGPU_TRY(cudaEventSynchronize(ds->ev_in[0]));
+    char *h = (char *)ds->h_mixed;
+    memset(h, 0, 64);                                         // three tickets
+    size_t off = 64;
+    size_t start[3];
+    for (int b = 0; b < 3; ++b) {
+        start[b] = off;
+        memcpy(h + off, bucket[b].data(), bucket[b].size() * sizeof(MixedItem));
+        off += bucket[b].size() * sizeof(MixedItem);
+    }
+    INVGPU_TRY(cudaMemcpyAsync(ds->d_mixed, h, off, cudaMemcpyHostToDevice, st));
+    INVGPU_TRY(cudaEventRecord(ds->ev_in[0], st));
+    cudaStream_t lanes[3] = {ds->s_in, ds->s_comp, ds->s_out};
+    char *d = (char *)ds->d_mixed;
+    for (int b = 2; b >= 0; --b) {                            // big matrices first
+        INVGPU_TRY(cudaStreamWaitEvent(lanes[b], ds->ev_in[0], 0));
+        const MixedItem *di = (const MixedItem *)(d + start[b]);
+        unsigned long long *tk = (unsigned long long *)(d + 16 * b);
+        if (b == 0) rc = launch_mixed_bucket<T, 32>(di, (i64)bucket[b].size(), nmax[b], dInfo, tk, lanes[b], ds);
+        else if (b == 1) rc = launch_mixed_bucket<T, 128>(di, (i64)bucket[b].size(), nmax[b], dInfo, tk, lanes[b], ds);
+        else rc = launch_mixed_bucket<T, 256>(di, (i64)bucket[b].size(), nmax[b], dInfo, tk, lanes[b], ds);
+        if (rc) return rc;
+        INVGPU_TRY(cudaEventRecord(ds->ev_comp[b], lanes[b]));
+        INVGPU_TRY(cudaStreamWaitEvent(st, ds->ev_comp[b], 0));
+    }
+    return 0;
+}
+
 }  // namespace invgpu
 
 using namespace invgpu;
@@ -404,6 +489,13 @@ int invgpu_gp_f64(int n, const double *dA, const double *dB, const double *dC, c
                   double *dMeans, double *dVariances, invgpu_i64 batch, int *dInfo, invgpu_stream_t s) {
     GpIO<double> io{dA, dB, dC, dD, dE, dMeans, dVariances};
     return run_gp<double>(io, n, batch, dInfo, (cudaStream_t)s);
+}
+
+int invgpu_mixed_spd_inverse_f32(float *const *As, float *const *Ainvs, const int *ns, invgpu_i64 count, int *dInfo, invgpu_stream_t s) {
+    return run_mixed_spd<float>(As, Ainvs, ns, count, dInfo, (cudaStream_t)s);
+}
+int invgpu_mixed_spd_inverse_f64(double *const *As, double *const *Ainvs, const int *ns, invgpu_i64 count, int *dInfo, invgpu_stream_t s) {
+    return run_mixed_spd<double>(As, Ainvs, ns, count, dInfo, (cudaStream_t)s);
 }
 
 static int finish_host(int rc, const int *info, const int *bad) {

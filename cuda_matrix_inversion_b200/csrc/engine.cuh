@@ -40,6 +40,9 @@ struct DeviceState {
     // scratch of the fused GP tile kernels (natural-order info recomputation of flagged matrices)
     void *gp_scratch = nullptr;
     size_t gp_scratch_bytes = 0;
+    // work lists of the mixed-dimension scheduler (device copy + pinned staging)
+    void *d_mixed = nullptr, *h_mixed = nullptr;
+    size_t mixed_bytes = 0;
 };
 
 DeviceState *device_state(int *err);   // state of the calling thread's current device

@@ -5,14 +5,18 @@
 #pragma once
 
 #ifndef INVGPU_F32_N32_MINB
-#define INVGPU_F32_N32_MINB 3
+#define INVGPU_F32_N32_MINB 2
+#endif
+#ifndef INVGPU_F32_N32_TR
+#define INVGPU_F32_N32_TR 4
+#define INVGPU_F32_N32_TC 2
 #endif
 
 // fp32 SPD inverse, warp tiers
 #define INVGPU_TILE_SPD_F32_INV(X)                              \
     X(float, 8, 1, 1, true, 7, 4)                               \
     X(float, 16, 2, 2, true, 7, 4)                              \
-    X(float, 32, 4, 2, true, 7, INVGPU_F32_N32_MINB)            \
+    X(float, 32, INVGPU_F32_N32_TR, INVGPU_F32_N32_TC, true, 7, INVGPU_F32_N32_MINB)            \
     X(float, 64, 8, 4, true, 7, 3)
 // fp32 SPD inverse, CTA tier
 #define INVGPU_TILE_SPD_F32_INV_CTA(X)                          \

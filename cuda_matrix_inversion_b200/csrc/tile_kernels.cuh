@@ -158,6 +158,15 @@ __device__ __forceinline__ void tile_sync() {
 #ifndef INVGPU_LOCKSTEP
 #define INVGPU_LOCKSTEP 8
 #endif
+// look-ahead variants of potrf / trtri (next pivot column published before the bulk update): measured
+// neutral to slightly negative on B200 (longer live ranges -> spills), kept for experiments
+#ifndef INVGPU_LOOKAHEAD
+#define INVGPU_LOOKAHEAD 0
+#endif
+// rolled pivot loops for square thread grids (see TileSpd::potrf_rolled)
+#ifndef INVGPU_ROLLED
+#define INVGPU_ROLLED 1
+#endif
 #ifndef INVGPU_LAUUM_SEG
 #define INVGPU_LAUUM_SEG 8
 #endif
@@ -179,6 +188,310 @@ struct TileSpd {
     // shared line offsets (memory order) of row group g / column group h of this thread
     static __device__ __forceinline__ int roff(int g, int ti) { return 4 * G::rblock(g, 0) + 4 * ti; }
     static __device__ __forceinline__ int coff(int h, int tj) { return 4 * G::cblock(h, 0) + 4 * tj; }
+
+    // =====================================================================================
+    // Warp-sized groups: phases with LOOK-AHEAD.  The next pivot column (row) is brought up to date,
+    // scaled and published before the bulk of the current rank-1 update, so the shuffle -> rsqrt ->
+    // scale -> store -> barrier -> load chain of step k+1 overlaps the FMAs of step k.
+    // =====================================================================================
+
+    // update of one column slot c by pivot k (rows with a logical index > k somewhere)
+    static __device__ __forceinline__ void potrf_update_col(T (&a)[SR][SC], const T (&lr)[SR], const T (&lc)[SC],
+                                                            int k, int c, int sk, int tj) {
+        if (G::cmax(c) <= k) return;
+        #pragma unroll
+        for (int r = 0; r < SR; ++r) {
+            if (G::rmax(r) <= k) continue;
+            if (G::cmin(c) > G::rmax(r)) continue;
+            if (c == sk) { if (clog(c, tj) > k) a[r][c] = fma(-lr[r], lc[c], a[r][c]); }
+            else a[r][c] = fma(-lr[r], lc[c], a[r][c]);
+        }
+    }
+
+    // pivot k: column k is up to date.  Fetch d, scale the column into L(:,k), publish it (+ y_k).
+    template <bool GP>
+    static __device__ __forceinline__ void potrf_publish(T (&a)[SR][SC], T (*z)[2], T *sm, int line_words, int k,
+                                                         int ti, int tj, int &info) {
+        T *cb = sm + (k & 1) * line_words;
+        const int ck = G::cowner(k), sk = G::cslot(k), rk = G::rowner(k), srk = G::rslot(k);
+        const int src = (threadIdx.x & 31 & ~(G::LANES - 1)) + rk * TC + ck;
+        const T d = __shfl_sync(0xffffffffu, a[srk][sk], src);
+        const T rs = dev_rsqrt<T>(d);
+        if (info == 0 && !(d > T(0))) info = k + 1;
+        if (tj == ck) {
+            #pragma unroll
+            for (int r = 0; r < SR; ++r)
+                if (G::rmax(r) >= k) a[r][sk] *= rs;               // row k itself: a_kk * rs = L_kk
+            if (k + 1 < N) {
+                #pragma unroll
+                for (int g = 0; g < SR / 4; ++g)
+                    if (G::sb_hi(g / G::QR, k))
+                        st4(cb + roff(g, ti), a[4 * g][sk], a[4 * g + 1][sk], a[4 * g + 2][sk], a[4 * g + 3][sk]);
+            }
+            if (ti == rk) {
+                if (GP) { cb[N] = z[srk][0] * rs; cb[N + 1] = z[srk][1] * rs; }
+                else sm[2 * N + G::memory(k)] = rs;                // 1 / L_kk for trtri
+            }
+        }
+    }
+
+    template <bool GP>
+    static __device__ __forceinline__ void potrf_la(T (&a)[SR][SC], T (*z)[2], T *sm, int ti, int tj, int &info,
+                                                    T &acc_m, T &acc_q) {
+        constexpr int LINE = GP ? N + 4 : N;
+        potrf_publish<GP>(a, z, sm, LINE, 0, ti, tj, info);
+        tile_sync<G::LANES>();
+        #pragma unroll
+        for (int k = 0; k < N; ++k) {
+            tile_lockstep<G::LANES>(k);
+            const T *cb = sm + (k & 1) * LINE;
+            const int sk = G::cslot(k);
+            T ya = T(0), yd = T(0);
+            if (GP) {
+                ya = cb[N]; yd = cb[N + 1];
+                acc_m = fma(ya, yd, acc_m);
+                acc_q = fma(ya, ya, acc_q);
+            }
+            if (k + 1 == N) break;
+            T lr[SR], lc[SC];
+            #pragma unroll
+            for (int g = 0; g < SR / 4; ++g)
+                if (G::sb_hi(g / G::QR, k))
+                    ld4(cb + roff(g, ti), lr[4 * g], lr[4 * g + 1], lr[4 * g + 2], lr[4 * g + 3]);
+            #pragma unroll
+            for (int g = 0; g < SC / 4; ++g)
+                if (G::sb_hi(g / G::QC, k))
+                    ld4(cb + coff(g, tj), lc[4 * g], lc[4 * g + 1], lc[4 * g + 2], lc[4 * g + 3]);
+            if (GP) {
+                #pragma unroll
+                for (int r = 0; r < SR; ++r) {
+                    if (G::rmax(r) <= k) continue;
+                    z[r][0] = fma(-lr[r], ya, z[r][0]);
+                    z[r][1] = fma(-lr[r], yd, z[r][1]);
+                }
+            }
+            const int sk1 = G::cslot(k + 1);
+            potrf_update_col(a, lr, lc, k, sk1, sk, tj);          // look-ahead: next pivot column first
+            potrf_publish<GP>(a, z, sm, LINE, k + 1, ti, tj, info);
+            #pragma unroll
+            for (int c = 0; c < SC; ++c)
+                if (c != sk1) potrf_update_col(a, lr, lc, k, c, sk, tj);
+            tile_sync<G::LANES>();
+        }
+    }
+
+    // row k of M is complete: finish it and park it in shared memory
+    static __device__ __forceinline__ void trtri_publish_row(T (&a)[SR][SC], const T *sm, T *mbuf, int k, int ti, int tj) {
+        const int rk = G::rowner(k), srk = G::rslot(k);
+        if (ti == rk) {
+            T *rb = mbuf + k * N;
+            const T rdk = sm[2 * N + G::memory(k)];
+            #pragma unroll
+            for (int c = 0; c < SC; ++c) {
+                if (G::cmin(c) > k) continue;
+                if (G::cmax(c) < k) a[srk][c] *= -rdk;
+                else {
+                    const int col = clog(c, tj);
+                    a[srk][c] = col < k ? a[srk][c] * -rdk : (col == k ? rdk : a[srk][c]);
+                }
+            }
+            #pragma unroll
+            for (int h = 0; h < SC / 4; ++h)
+                if (G::sb_lo(h / G::QC, k))
+                    st4(rb + coff(h, tj), a[srk][4 * h], a[srk][4 * h + 1], a[srk][4 * h + 2], a[srk][4 * h + 3]);
+        }
+    }
+    // column k of L (rows > k): publish, then clear it for the accumulation of M
+    static __device__ __forceinline__ void trtri_publish_col(T (&a)[SR][SC], T *sm, int k, int ti, int tj) {
+        const int ck = G::cowner(k), sk = G::cslot(k);
+        if (tj == ck) {
+            T *cb = sm + (k & 1) * N;
+            #pragma unroll
+            for (int g = 0; g < SR / 4; ++g)
+                if (G::sb_hi(g / G::QR, k))
+                    st4(cb + roff(g, ti), a[4 * g][sk], a[4 * g + 1][sk], a[4 * g + 2][sk], a[4 * g + 3][sk]);
+            #pragma unroll
+            for (int r = 0; r < SR; ++r) {
+                if (G::rmax(r) <= k) continue;
+                if (G::rmin(r) > k) a[r][sk] = T(0);
+                else a[r][sk] = rlog(r, ti) > k ? T(0) : a[r][sk];
+            }
+        }
+    }
+    static __device__ __forceinline__ void trtri_update_row(T (&a)[SR][SC], const T (&lr)[SR], const T (&mr)[SC], int k, int r) {
+        if (G::rmax(r) <= k) return;
+        #pragma unroll
+        for (int c = 0; c < SC; ++c) {
+            if (G::cmin(c) > k) continue;
+            a[r][c] = fma(lr[r], mr[c], a[r][c]);
+        }
+    }
+    static __device__ __forceinline__ void trtri_la(T (&a)[SR][SC], T *sm, T *mbuf, int ti, int tj) {
+        trtri_publish_row(a, sm, mbuf, 0, ti, tj);
+        if (N > 1) trtri_publish_col(a, sm, 0, ti, tj);
+        tile_sync<G::LANES>();
+        #pragma unroll
+        for (int k = 0; k + 1 < N; ++k) {
+            tile_lockstep<G::LANES>(k);
+            const T *cb = sm + (k & 1) * N;
+            const T *rb = mbuf + k * N;
+            const int rk = G::rowner(k), srk = G::rslot(k);
+            T lr[SR], mr[SC];
+            #pragma unroll
+            for (int g = 0; g < SR / 4; ++g)
+                if (G::sb_hi(g / G::QR, k))
+                    ld4(cb + roff(g, ti), lr[4 * g], lr[4 * g + 1], lr[4 * g + 2], lr[4 * g + 3]);
+            if (ti == rk) lr[srk] = T(0);                          // row k is finished: leave it alone
+            #pragma unroll
+            for (int h = 0; h < SC / 4; ++h)
+                if (G::sb_lo(h / G::QC, k))
+                    ld4(rb + coff(h, tj), mr[4 * h], mr[4 * h + 1], mr[4 * h + 2], mr[4 * h + 3]);
+            const int srk1 = G::rslot(k + 1);
+            trtri_update_row(a, lr, mr, k, srk1);                  // look-ahead: next row of M first
+            trtri_publish_row(a, sm, mbuf, k + 1, ti, tj);
+            if (k + 2 < N) trtri_publish_col(a, sm, k + 1, ti, tj);
+            #pragma unroll
+            for (int r = 0; r < SR; ++r)
+                if (r != srk1) trtri_update_row(a, lr, mr, k, r);
+            tile_sync<G::LANES>();
+        }
+    }
+
+    // =====================================================================================
+    // Square thread grids (TR == TC == P, permuted order): the P consecutive pivots k = P*s + t,
+    // t = 0..P-1, all live in register slot (s, s) of the diagonal threads (t, t), and the set of
+    // active slots is the same for all of them.  So the pivot loop is ROLLED over t (run-time owner
+    // tests, static register indices): N/P small bodies instead of N -- for n = 128 the difference
+    // between ~25 thousand and ~1 thousand instructions of code.
+    // =====================================================================================
+    template <bool GP>
+    static __device__ __forceinline__ void potrf_rolled(T (&a)[SR][SC], T (*z)[2], T *sm, int ti, int tj, int &info,
+                                                        T &acc_m, T &acc_q) {
+        static_assert(TR == TC && PERM, "rolled phases need a square thread grid and the cyclic order");
+        constexpr int LINE = GP ? N + 4 : N;
+        #pragma unroll
+        for (int s = 0; s < SR; ++s) {
+            const int kbase = G::P * s;                          // logical index of slot s in thread 0
+            const int mbase = 4 * (G::P * (s / 4)) + (s % 4);     // its memory index; thread t adds 4 t
+            #pragma unroll 1
+            for (int t = 0; t < G::P; ++t) {
+                const int k = kbase + t;
+                T *cb = sm + (k & 1) * LINE;
+                T d, rs;
+                if (G::LANES <= 32) {
+                    const int src = (threadIdx.x & 31 & ~(G::LANES - 1)) + t * TC + t;
+                    d = __shfl_sync(0xffffffffu, a[s][s], src);
+                    rs = dev_rsqrt<T>(d);
+                    if (tj == t) {
+                        #pragma unroll
+                        for (int r = s; r < SR; ++r) a[r][s] *= rs;
+                        #pragma unroll
+                        for (int g = s / 4; g < SR / 4; ++g)
+                            st4(cb + roff(g, ti), a[4 * g][s], a[4 * g + 1][s], a[4 * g + 2][s], a[4 * g + 3][s]);
+                        if (ti == t) {
+                            if (GP) { cb[N] = z[s][0] * rs; cb[N + 1] = z[s][1] * rs; }
+                            else sm[2 * N + mbase + 4 * t] = rs;
+                        }
+                    }
+                    tile_sync<G::LANES>();
+                } else {
+                    if (tj == t) {
+                        #pragma unroll
+                        for (int g = s / 4; g < SR / 4; ++g)
+                            st4(cb + roff(g, ti), a[4 * g][s], a[4 * g + 1][s], a[4 * g + 2][s], a[4 * g + 3][s]);
+                        if (ti == t) {                             // the diagonal thread owns the pivot itself
+                            const T r0 = dev_rsqrt<T>(a[s][s]);
+                            if (GP) { cb[N] = z[s][0] * r0; cb[N + 1] = z[s][1] * r0; }
+                            else sm[2 * N + mbase + 4 * t] = r0;
+                        }
+                    }
+                    tile_sync<G::LANES>();
+                    d = cb[mbase + 4 * t];
+                    rs = dev_rsqrt<T>(d);
+                    if (tj == t) {
+                        #pragma unroll
+                        for (int r = s; r < SR; ++r) a[r][s] *= rs;
+                    }
+                }
+                if (info == 0 && !(d > T(0))) info = k + 1;
+                T ya = T(0), yd = T(0);
+                if (GP) {
+                    ya = cb[N]; yd = cb[N + 1];
+                    acc_m = fma(ya, yd, acc_m);
+                    acc_q = fma(ya, ya, acc_q);
+                }
+                if (k + 1 == N) break;
+                T lr[SR], lc[SC];
+                #pragma unroll
+                for (int g = s / 4; g < SR / 4; ++g) {
+                    ld4(cb + roff(g, ti), lr[4 * g], lr[4 * g + 1], lr[4 * g + 2], lr[4 * g + 3]);
+                    ld4(cb + coff(g, tj), lc[4 * g], lc[4 * g + 1], lc[4 * g + 2], lc[4 * g + 3]);
+                    if (G::LANES > 32) {
+                        #pragma unroll
+                        for (int w = 0; w < 4; ++w) { lr[4 * g + w] *= rs; lc[4 * g + w] *= rs; }
+                    }
+                }
+                #pragma unroll
+                for (int r = s; r < SR; ++r) {
+                    if (GP) {
+                        z[r][0] = fma(-lr[r], ya, z[r][0]);
+                        z[r][1] = fma(-lr[r], yd, z[r][1]);
+                    }
+                    #pragma unroll
+                    for (int c = s; c <= r; ++c) {                 // lower part: column slot <= row slot
+                        if (c == s) { if (tj > t) a[r][c] = fma(-lr[r], lc[c], a[r][c]); }
+                        else a[r][c] = fma(-lr[r], lc[c], a[r][c]);
+                    }
+                }
+            }
+        }
+    }
+
+    static __device__ __forceinline__ void trtri_rolled(T (&a)[SR][SC], T *sm, T *mbuf, int ti, int tj) {
+        static_assert(TR == TC && PERM, "rolled phases need a square thread grid and the cyclic order");
+        #pragma unroll
+        for (int s = 0; s < SR; ++s) {
+            const int kbase = G::P * s;
+            const int mbase = 4 * (G::P * (s / 4)) + (s % 4);
+            #pragma unroll 1
+            for (int t = 0; t < G::P; ++t) {
+                const int k = kbase + t;
+                T *cb = sm + (k & 1) * N;
+                T *rb = mbuf + k * N;
+                if (ti == t) {                                     // owners of row k: finish and park it
+                    const T rdk = sm[2 * N + mbase + 4 * t];
+                    #pragma unroll
+                    for (int c = 0; c < s; ++c) a[s][c] *= -rdk;   // columns < kbase <= k
+                    a[s][s] = tj < t ? a[s][s] * -rdk : (tj == t ? rdk : a[s][s]);
+                    #pragma unroll
+                    for (int h = 0; h <= s / 4; ++h)
+                        st4(rb + coff(h, tj), a[s][4 * h], a[s][4 * h + 1], a[s][4 * h + 2], a[s][4 * h + 3]);
+                }
+                if (k + 1 == N) break;
+                if (tj == t) {                                     // column k of L, rows > k: publish, then clear
+                    #pragma unroll
+                    for (int g = s / 4; g < SR / 4; ++g)
+                        st4(cb + roff(g, ti), a[4 * g][s], a[4 * g + 1][s], a[4 * g + 2][s], a[4 * g + 3][s]);
+                    a[s][s] = ti > t ? T(0) : a[s][s];
+                    #pragma unroll
+                    for (int r = s + 1; r < SR; ++r) a[r][s] = T(0);
+                }
+                tile_sync<G::LANES>();
+                T lr[SR], mr[SC];
+                #pragma unroll
+                for (int g = s / 4; g < SR / 4; ++g)
+                    ld4(cb + roff(g, ti), lr[4 * g], lr[4 * g + 1], lr[4 * g + 2], lr[4 * g + 3]);
+                lr[s] = ti > t ? lr[s] : T(0);                     // rows <= k of this slot are finished
+                #pragma unroll
+                for (int h = 0; h <= s / 4; ++h)
+                    ld4(rb + coff(h, tj), mr[4 * h], mr[4 * h + 1], mr[4 * h + 2], mr[4 * h + 3]);
+                #pragma unroll
+                for (int r = s; r < SR; ++r)
+                    #pragma unroll
+                    for (int c = 0; c <= s; ++c) a[r][c] = fma(lr[r], mr[c], a[r][c]);
+            }
+        }
+    }
 
     // ---- potrf ---------------------------------------------------------------------------
     // the line sm[2N + i] receives 1 / L_ii (memory index i) for trtri
@@ -508,6 +821,17 @@ struct TileSpd {
     }
 };
 
+// Calls into the rolled phases only when the geometry allows them (keeps their static_asserts
+// out of rectangular instantiations).
+template <typename K, bool GP, typename T, int SR, int SC>
+__device__ __forceinline__ void tile_potrf_rolled(T (&a)[SR][SC], T (*z)[2], T *sm, int ti, int tj, int &info, T &m, T &q) {
+    if constexpr (SR == SC) K::template potrf_rolled<GP>(a, z, sm, ti, tj, info, m, q);
+}
+template <typename K, typename T, int SR, int SC>
+__device__ __forceinline__ void tile_trtri_rolled(T (&a)[SR][SC], T *sm, T *mbuf, int ti, int tj) {
+    if constexpr (SR == SC) K::trtri_rolled(a, sm, mbuf, ti, tj);
+}
+
 // Natural-order spotrf info of one matrix, computed by a single thread using the (about to be
 // NaN-filled) output matrix as scratch.  Only reached for matrices the fast path flagged.
 template <typename T>
@@ -622,13 +946,23 @@ tile_spd_kernel(IO io, i64 batch, int *__restrict__ info) {
         tile_load_upper<T, N, TR, TC, PERM>(a, src, ti, tj);
 
         int st = 0;
-        K::potrf(a, sm, ti, tj, st);
+#ifndef INVGPU_DEBUG_SKIP_COMPUTE      // debug: memory-pattern floor of the kernel (load + store only)
+        if (TR == TC && PERM && INVGPU_ROLLED) { T dm = T(0), dq = T(0); tile_potrf_rolled<K, false>(a, (T(*)[2]) nullptr, sm, ti, tj, st, dm, dq); }
+        else if (G::LANES <= 32 && INVGPU_LOOKAHEAD) { T dm = T(0), dq = T(0); K::template potrf_la<false>(a, nullptr, sm, ti, tj, st, dm, dq); }
+        else K::potrf(a, sm, ti, tj, st);
+#ifndef INVGPU_DEBUG_ONLY_POTRF
         if (STAGES & SPD_TRTRI) {
             K::clear_upper(a, ti, tj);
             tile_sync<G::LANES>();
-            K::trtri(a, sm, sm + G::LINES, ti, tj);
+            if (TR == TC && PERM && INVGPU_ROLLED) tile_trtri_rolled<K>(a, sm, sm + G::LINES, ti, tj);
+            else if (G::LANES <= 32 && INVGPU_LOOKAHEAD) K::trtri_la(a, sm, sm + G::LINES, ti, tj);
+            else K::trtri(a, sm, sm + G::LINES, ti, tj);
         }
+#ifndef INVGPU_DEBUG_NO_LAUUM
         if (STAGES & SPD_LAUUM) { tile_sync<G::LANES>(); K::lauum(a, sm + G::LINES, ti, tj); }
+#endif
+#endif
+#endif
         tile_sync<G::LANES>();                       // shared lines are reused by the next matrix
 
         if (!valid) continue;
@@ -727,7 +1061,9 @@ tile_gp_kernel(GpIO<T> io, i64 batch, int *__restrict__ info, T *__restrict__ sc
 
         int st = 0;
         T acc_m = T(0), acc_q = T(0);
-        K::potrf_gp(a, z, sm, ti, tj, st, acc_m, acc_q);
+        if (TR == TC && INVGPU_ROLLED) tile_potrf_rolled<K, true>(a, z, sm, ti, tj, st, acc_m, acc_q);
+        else if (G::LANES <= 32 && INVGPU_LOOKAHEAD) K::template potrf_la<true>(a, z, sm, ti, tj, st, acc_m, acc_q);
+        else K::potrf_gp(a, z, sm, ti, tj, st, acc_m, acc_q);
         tile_sync<G::LANES>();
 
         if (!valid) continue;

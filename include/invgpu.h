@@ -76,6 +76,17 @@ int invgpu_spd_stages_ptrs_f64(double *const *As, double *const *Outs, int n, in
 int invgpu_general_inverse_ptrs_f32(float *const *As, float *const *Ainvs, int n, int batch, int *dInfo, invgpu_stream_t stream);
 int invgpu_general_inverse_ptrs_f64(double *const *As, double *const *Ainvs, int n, int batch, int *dInfo, invgpu_stream_t stream);
 
+/* ---- mixed dimensions: persistent-CTA scheduler ------------------------------------------- *
+ * SPD inverse of `count` matrices of individual order ns[i] (1..256; fp64: as far as a packed
+ * triangle fits one CTA's shared memory, n <= 236).  As / Ainvs / ns are HOST arrays; As[i] / Ainvs[i]
+ * are DEVICE pointers (column-major, lda = ns[i]).  The work is bucketed by size (<= 32, <= 128,
+ * <= 256 -- the reference README's "size-bucketed stream queues", README.md:41-44) and every bucket is
+ * drained by a persistent grid pulling work with an atomic ticket, longest matrices first; the three
+ * bucket kernels run concurrently.  Asynchronous with respect to `stream` once the work list is
+ * uploaded; dInfo[i] (device, may be NULL) follows the caller's order. */
+int invgpu_mixed_spd_inverse_f32(float *const *As, float *const *Ainvs, const int *ns, invgpu_i64 count, int *dInfo, invgpu_stream_t stream);
+int invgpu_mixed_spd_inverse_f64(double *const *As, double *const *Ainvs, const int *ns, invgpu_i64 count, int *dInfo, invgpu_stream_t stream);
+
 /* ---- fused GP mean / variance, dense device batches -------------------------------------- *
  * means[i] = A_i^T (B_i + diag C_i)^-1 D_i ; variances[i] = E_i - A_i^T (B_i + diag C_i)^-1 A_i.
  * ONE kernel replaces addDiagonal -> batchedInverse -> batchedMul -> batchedMul

@@ -360,6 +360,42 @@ def test_legacy_device_entry_points(api, torch, ptrs_on):
     assert normwise_err(out(), np.linalg.cholesky(a.astype(np.float64))) <= 1e-4
 
 
+# --------------------------------------------------------------------------------------- mixed dimensions
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_mixed_dimension_scheduler(api, torch, dtype):
+    """BASELINE config 5 in miniature: sizes drawn from the 32 / 128 / 256 buckets, one call."""
+    rng = np.random.default_rng(777)
+    top = 256 if dtype == np.float32 else 200
+    ns = np.concatenate([rng.integers(1, 33, 150), rng.integers(33, 129, 40), rng.integers(129, top + 1, 10)])
+    rng.shuffle(ns)
+    mats = [spd_batch(int(n), 1, dtype, seed=int(1000 + i))[0] for i, n in enumerate(ns)]
+    offs = np.concatenate([[0], np.cumsum([m.size for m in mats])])
+    flat = np.concatenate([m.reshape(-1) for m in mats])
+    bad = 17                                                   # one non-SPD matrix in the middle
+    n_bad = int(ns[bad])
+    flat[offs[bad]:offs[bad + 1]] = -np.eye(n_bad, dtype=dtype).reshape(-1)
+    d_in = torch.from_numpy(flat).cuda()
+    d_out = torch.zeros_like(d_in)
+    d_info = torch.full((len(ns),), -1, dtype=torch.int32, device="cuda")
+    esz = flat.itemsize
+    pin = np.array([d_in.data_ptr() + int(o) * esz for o in offs[:-1]], dtype=np.uint64)
+    pout = np.array([d_out.data_ptr() + int(o) * esz for o in offs[:-1]], dtype=np.uint64)
+    api.mixed_spd_inverse_device(pin, pout, ns, dtype, d_info.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    info = d_info.cpu().numpy()
+    out = d_out.cpu().numpy()
+    assert info[bad] == 1 and (np.delete(info, bad) == 0).all()
+    assert np.isnan(out[offs[bad]:offs[bad + 1]]).all()
+    tol = TOL[np.dtype(dtype)]
+    for i, n in enumerate(ns):
+        if i == bad:
+            continue
+        n = int(n)
+        want, _ = orc.chol_inverse(flat[offs[i]:offs[i + 1]], n)
+        got = out[offs[i]:offs[i + 1]]
+        assert np.abs(got - want).max() <= tol * np.abs(want).max(), (i, n)
+
+
 # --------------------------------------------------------------------------------------- host pipeline
 def test_host_pipeline_chunking_and_pinned_path(api, torch, monkeypatch):
     """Many chunks, ragged last chunk, pageable and pinned user buffers give identical results."""

@@ -83,6 +83,31 @@ __device__ __forceinline__ void stg4(double *p, double a, double b, double c, do
     __stcs(reinterpret_cast<double2 *>(p + 2), make_double2(c, d));
 }
 
+// Two FMAs in one instruction slot: (x0, x1) += (l0, l1) * c.  On sm_100a this is one FFMA2 with the
+// scalar operand broadcast (R.F32) and an optional negation folded into the packed operand; the two
+// accumulators are vertically adjacent tile elements, which is also what the 128-bit stores want.
+#ifndef INVGPU_FFMA2
+#define INVGPU_FFMA2 0   // measured on B200: the kernels are not issue-bound, FFMA2 buys nothing and its
+                         // register-pair constraints add moves (n = 128: 8.5 ms vs 7.7 ms); kept for experiments
+#endif
+__device__ __forceinline__ void fma2_rows(float &x0, float &x1, float l0, float l1, float c) {
+#if !INVGPU_FFMA2
+    x0 = fmaf(l0, c, x0);
+    x1 = fmaf(l1, c, x1);
+    return;
+#endif
+    unsigned long long acc, ll, cc;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(acc) : "f"(x0), "f"(x1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ll) : "f"(l0), "f"(l1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(cc) : "f"(c), "f"(c));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(ll), "l"(cc));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(acc));
+}
+__device__ __forceinline__ void fma2_rows(double &x0, double &x1, double l0, double l1, double c) {
+    x0 = fma(l0, c, x0);
+    x1 = fma(l1, c, x1);
+}
+
 template <typename T> __device__ __forceinline__ T dev_rcp(T x);
 template <> __device__ __forceinline__ float dev_rcp<float>(float x) { return __frcp_rn(x); }
 template <> __device__ __forceinline__ double dev_rcp<double>(double x) { return 1.0 / x; }
@@ -432,15 +457,15 @@ struct TileSpd {
                     }
                 }
                 #pragma unroll
-                for (int r = s; r < SR; ++r) {
+                for (int r = s & ~1; r < SR; r += 2) {             // row pairs (slot s may be the odd one of its pair)
                     if (GP) {
-                        z[r][0] = fma(-lr[r], ya, z[r][0]);
-                        z[r][1] = fma(-lr[r], yd, z[r][1]);
+                        fma2_rows(z[r][0], z[r + 1][0], -lr[r], -lr[r + 1], ya);
+                        fma2_rows(z[r][1], z[r + 1][1], -lr[r], -lr[r + 1], yd);
                     }
                     #pragma unroll
-                    for (int c = s; c <= r; ++c) {                 // lower part: column slot <= row slot
-                        if (c == s) { if (tj > t) a[r][c] = fma(-lr[r], lc[c], a[r][c]); }
-                        else a[r][c] = fma(-lr[r], lc[c], a[r][c]);
+                    for (int c = s; c <= r + 1; ++c) {             // lower part: column slot <= row slot
+                        if (c == s) { if (tj > t) fma2_rows(a[r][c], a[r + 1][c], -lr[r], -lr[r + 1], lc[c]); }
+                        else fma2_rows(a[r][c], a[r + 1][c], -lr[r], -lr[r + 1], lc[c]);
                     }
                 }
             }
@@ -486,9 +511,11 @@ struct TileSpd {
                 for (int h = 0; h <= s / 4; ++h)
                     ld4(rb + coff(h, tj), mr[4 * h], mr[4 * h + 1], mr[4 * h + 2], mr[4 * h + 3]);
                 #pragma unroll
-                for (int r = s; r < SR; ++r)
+                for (int r = s & ~1; r < SR; r += 2) {
+                    const T l0 = r < s ? T(0) : lr[r];             // slot below s: rows already finished
                     #pragma unroll
-                    for (int c = 0; c <= s; ++c) a[r][c] = fma(lr[r], mr[c], a[r][c]);
+                    for (int c = 0; c <= s; ++c) fma2_rows(a[r][c], a[r + 1][c], l0, lr[r + 1], mr[c]);
+                }
             }
         }
     }
@@ -559,16 +586,16 @@ struct TileSpd {
                     }
                 }
             #pragma unroll
-            for (int r = 0; r < SR; ++r) {
-                if (G::rmax(r) <= k) continue;
+            for (int r = 0; r < SR; r += 2) {                      // row pairs: one FFMA2 per two elements
+                if (G::rmax(r + 1) <= k) continue;
                 #pragma unroll
                 for (int c = 0; c < SC; ++c) {
                     if (G::cmax(c) <= k) continue;                 // column already final everywhere
-                    if (G::cmin(c) > G::rmax(r)) continue;         // strictly upper for every thread
+                    if (G::cmin(c) > G::rmax(r + 1)) continue;     // strictly upper for every thread
                     if (c == sk) {                                  // slot that holds column k in its owners
-                        if (clog(c, tj) > k) a[r][c] = fma(-lr[r], lc[c], a[r][c]);
+                        if (clog(c, tj) > k) fma2_rows(a[r][c], a[r + 1][c], -lr[r], -lr[r + 1], lc[c]);
                     } else {
-                        a[r][c] = fma(-lr[r], lc[c], a[r][c]);
+                        fma2_rows(a[r][c], a[r + 1][c], -lr[r], -lr[r + 1], lc[c]);
                     }
                 }
             }
@@ -647,18 +674,18 @@ struct TileSpd {
                     }
                 }
             #pragma unroll
-            for (int r = 0; r < SR; ++r) {
-                if (G::rmax(r) <= k) continue;
-                z[r][0] = fma(-lr[r], ya, z[r][0]);
-                z[r][1] = fma(-lr[r], yd, z[r][1]);
+            for (int r = 0; r < SR; r += 2) {
+                if (G::rmax(r + 1) <= k) continue;
+                fma2_rows(z[r][0], z[r + 1][0], -lr[r], -lr[r + 1], ya);
+                fma2_rows(z[r][1], z[r + 1][1], -lr[r], -lr[r + 1], yd);
                 #pragma unroll
                 for (int c = 0; c < SC; ++c) {
                     if (G::cmax(c) <= k) continue;
-                    if (G::cmin(c) > G::rmax(r)) continue;
+                    if (G::cmin(c) > G::rmax(r + 1)) continue;
                     if (c == sk) {
-                        if (clog(c, tj) > k) a[r][c] = fma(-lr[r], lc[c], a[r][c]);
+                        if (clog(c, tj) > k) fma2_rows(a[r][c], a[r + 1][c], -lr[r], -lr[r + 1], lc[c]);
                     } else {
-                        a[r][c] = fma(-lr[r], lc[c], a[r][c]);
+                        fma2_rows(a[r][c], a[r + 1][c], -lr[r], -lr[r + 1], lc[c]);
                     }
                 }
             }
@@ -731,12 +758,14 @@ struct TileSpd {
                 if (G::sb_lo(h / G::QC, k))
                     ld4(rb + coff(h, tj), mr[4 * h], mr[4 * h + 1], mr[4 * h + 2], mr[4 * h + 3]);
             #pragma unroll
-            for (int r = 0; r < SR; ++r) {
-                if (G::rmax(r) <= k) continue;
+            for (int r = 0; r < SR; r += 2) {
+                if (G::rmax(r + 1) <= k) continue;
+                // a row of the pair that is already finished (<= k) must stay untouched
+                const T l0 = G::rmax(r) <= k ? T(0) : lr[r];
                 #pragma unroll
                 for (int c = 0; c < SC; ++c) {
                     if (G::cmin(c) > k) continue;
-                    a[r][c] = fma(lr[r], mr[c], a[r][c]);
+                    fma2_rows(a[r][c], a[r + 1][c], l0, lr[r + 1], mr[c]);
                 }
             }
         }
@@ -783,12 +812,13 @@ struct TileSpd {
                             ld4(rb + coff(h, tj), mc[4 * h], mc[4 * h + 1], mc[4 * h + 2], mc[4 * h + 3]);
                     }
                 #pragma unroll
-                for (int r = 0; r < SR; ++r) {
+                for (int r = 0; r < SR; r += 2) {
                     if (G::rmin(r) > k1) continue;
+                    const T m1 = G::rmin(r + 1) > k1 ? T(0) : mi[r + 1];   // not loaded yet -> contributes nothing
                     #pragma unroll
                     for (int c = 0; c < SC; ++c) {
                         if (G::cmin(c) > k1) continue;
-                        a[r][c] = fma(mi[r], mc[c], a[r][c]);
+                        fma2_rows(a[r][c], a[r + 1][c], mi[r], m1, mc[c]);
                     }
                 }
             }
@@ -808,12 +838,13 @@ struct TileSpd {
                 if (G::sb_lo(h / G::QC, k))
                     ld4(rb + coff(h, tj), mc[4 * h], mc[4 * h + 1], mc[4 * h + 2], mc[4 * h + 3]);
             #pragma unroll
-            for (int r = 0; r < SR; ++r) {
+            for (int r = 0; r < SR; r += 2) {
                 if (G::rmin(r) > k) continue;
+                const T m1 = G::rmin(r + 1) > k ? T(0) : mi[r + 1];
                 #pragma unroll
                 for (int c = 0; c < SC; ++c) {
                     if (G::cmin(c) > k) continue;
-                    a[r][c] = fma(mi[r], mc[c], a[r][c]);
+                    fma2_rows(a[r][c], a[r + 1][c], mi[r], m1, mc[c]);
                 }
             }
         }

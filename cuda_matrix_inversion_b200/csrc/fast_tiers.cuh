@@ -27,9 +27,21 @@ static bool dense_aligned(const StridedIO<T> &io, int n) {
         return launch_tile_spd<TT, N, TR, TC, PERM, STAGES_, MINB>(                                  \
             *reinterpret_cast<StridedIO<TT> *>(&io), batch, dInfo, st, ds);
 
+#define INVGPU_ONESWEEP_TRY(TT, N, TR, TC, STAGE, MINB)                                             \
+    if (std::is_same<T, TT>::value && n == N)                                                        \
+        return launch_onesweep<TT, N, TR, TC, STAGE, MINB>(*reinterpret_cast<StridedIO<TT> *>(&io), batch, dInfo, st, ds);
+
+// INVGPU_SPD_KERNEL=threesweep selects the three-sweep tile kernels for the sizes both families cover
+static bool prefer_onesweep() {
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("INVGPU_SPD_KERNEL"); v = (e && !strcmp(e, "threesweep")) ? 0 : 1; }
+    return v == 1;
+}
+
 template <typename T, int STAGES>
 static int fast_spd_dense(StridedIO<T> io, int n, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds) {
     if (!dense_aligned(io, n)) return INVGPU_NO_FAST_PATH;
+    if (STAGES == SPD_INVERSE && prefer_onesweep()) { INVGPU_ONESWEEP_ALL(INVGPU_ONESWEEP_TRY) }
     INVGPU_TILE_SPD_ALL(INVGPU_TILE_TRY)
     return INVGPU_NO_FAST_PATH;
 }

@@ -50,3 +50,17 @@
 #define INVGPU_GJ_F32(X) X(float, 8, 1, 4) X(float, 16, 1, 4) X(float, 32, 1, 4)
 #define INVGPU_GJ_F64(X) X(double, 8, 1, 4) X(double, 16, 1, 4) X(double, 32, 1, 3)
 #define INVGPU_GJ_ALL(X) INVGPU_GJ_F32(X) INVGPU_GJ_F64(X)
+
+// SPD inverse, one-sweep Cholesky (onesweep_kernels.cuh), warp tiers:  X(T, N, TR, TC, STAGE, MINB)
+#ifndef INVGPU_OS_F32_N32_MINB
+#define INVGPU_OS_F32_N32_MINB 5
+#endif
+#ifndef INVGPU_OS_F32_N32_TR
+#define INVGPU_OS_F32_N32_TR 4
+#define INVGPU_OS_F32_N32_TC 4
+#endif
+// (n = 64 stays on the three-sweep kernel: without compile-time pruning of the shrinking trailing
+//  matrix the one-sweep form does more FMAs, and at n = 64 the kernel is no longer latency-bound)
+#define INVGPU_ONESWEEP_F32(X) X(float, 8, 1, 1, true, 4) X(float, 16, 2, 2, false, 4) X(float, 32, INVGPU_OS_F32_N32_TR, INVGPU_OS_F32_N32_TC, false, INVGPU_OS_F32_N32_MINB)
+#define INVGPU_ONESWEEP_F64(X) X(double, 8, 1, 1, true, 2) X(double, 16, 2, 2, false, 2) X(double, 32, 4, 4, false, 2)
+#define INVGPU_ONESWEEP_ALL(X) INVGPU_ONESWEEP_F32(X) INVGPU_ONESWEEP_F64(X)

@@ -16,13 +16,31 @@ int launch_tile_gp(GpIO<T> io, i64 batch, int *dInfo, cudaStream_t st, DeviceSta
 template <typename T, int N, int ROWS, typename IO, int MINB>
 int launch_gj(IO io, int n, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds);
 
+template <typename T, int N, int TR, int TC, bool STAGE, int MINB>
+int launch_onesweep(StridedIO<T> io, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds);
+
 }  // namespace invgpu
 
 #ifdef INVGPU_TILE_DEFINE
 #include "tile_kernels.cuh"
 #include "gj_kernels.cuh"
+#include "onesweep_kernels.cuh"
 
 namespace invgpu {
+
+template <typename T, int N, int TR, int TC, bool STAGE, int MINB>
+int launch_onesweep(StridedIO<T> io, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds) {
+    using G = TileGeo<N, TR, TC, false>;
+    auto kern = onesweep_spd_kernel<T, N, TR, TC, STAGE, StridedIO<T>, MINB>;
+    constexpr int WORDS = ((2 * N + 31) / 32) * 32 + (G::LANES < 32 ? 8 : 0) + (STAGE ? TileStage<T, N, TR, TC>::MATRIX_WORDS : 0);
+    const size_t smem = (size_t)G::MPB * WORDS * sizeof(T);
+    int grid = 0;
+    int rc = persistent_grid(kern, G::BLOCK, smem, (batch + G::MPB - 1) / G::MPB, ds, &grid);
+    if (rc) return rc;
+    kern<<<grid, G::BLOCK, smem, st>>>(io, batch, dInfo);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return (int)cudaGetLastError();
+}
 
 template <typename T, int N, int ROWS, typename IO, int MINB>
 int launch_gj(IO io, int n, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds) {
@@ -83,6 +101,8 @@ int launch_tile_gp(GpIO<T> io, i64 batch, int *dInfo, cudaStream_t st, DeviceSta
 #define INVGPU_GJ_INSTANTIATE(T, N, ROWS, MINB) \
     template int invgpu::launch_gj<T, N, ROWS, invgpu::StridedIO<T>, MINB>(invgpu::StridedIO<T>, int, invgpu::i64, int *, cudaStream_t, invgpu::DeviceState *); \
     template int invgpu::launch_gj<T, N, ROWS, invgpu::PtrIO<T>, MINB>(invgpu::PtrIO<T>, int, invgpu::i64, int *, cudaStream_t, invgpu::DeviceState *);
+#define INVGPU_ONESWEEP_INSTANTIATE(T, N, TR, TC, STAGE, MINB) \
+    template int invgpu::launch_onesweep<T, N, TR, TC, STAGE, MINB>(invgpu::StridedIO<T>, invgpu::i64, int *, cudaStream_t, invgpu::DeviceState *);
 #define INVGPU_TILE_INSTANTIATE_GP(T, N, TR, TC, MINB) \
     template int invgpu::launch_tile_gp<T, N, TR, TC, MINB>(invgpu::GpIO<T>, invgpu::i64, int *, cudaStream_t, invgpu::DeviceState *);
 #endif

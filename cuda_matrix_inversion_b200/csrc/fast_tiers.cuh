@@ -31,6 +31,10 @@ static bool dense_aligned(const StridedIO<T> &io, int n) {
     if (std::is_same<T, TT>::value && n == N)                                                        \
         return launch_onesweep<TT, N, TR, TC, STAGE, MINB>(*reinterpret_cast<StridedIO<TT> *>(&io), batch, dInfo, st, ds);
 
+#define INVGPU_OSR_TRY(TT, N, P, MINB)                                                              \
+    if (std::is_same<T, TT>::value && n == N)                                                        \
+        return launch_onesweep_rolled<TT, N, P, MINB>(*reinterpret_cast<StridedIO<TT> *>(&io), batch, dInfo, st, ds);
+
 // INVGPU_SPD_KERNEL=threesweep selects the three-sweep tile kernels for the sizes both families cover
 static bool prefer_onesweep() {
     static int v = -1;
@@ -41,7 +45,14 @@ static bool prefer_onesweep() {
 template <typename T, int STAGES>
 static int fast_spd_dense(StridedIO<T> io, int n, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds) {
     if (!dense_aligned(io, n)) return INVGPU_NO_FAST_PATH;
-    if (STAGES == SPD_INVERSE && prefer_onesweep()) { INVGPU_ONESWEEP_ALL(INVGPU_ONESWEEP_TRY) }
+    if (STAGES == SPD_INVERSE && prefer_onesweep()) {
+        // n >= 64: the rolled sweep kernel (sweep_kernels.cuh); n <= 32: the fully unrolled one-sweep kernel.
+        // INVGPU_SPD_KERNEL=rolled prefers the rolled kernel wherever it is instantiated (experiments).
+        static int rolled = -1;
+        if (rolled < 0) { const char *e = getenv("INVGPU_SPD_KERNEL"); rolled = (e && !strcmp(e, "rolled")) ? 1 : 0; }
+        if (rolled || n >= 64) { INVGPU_OSR_ALL(INVGPU_OSR_TRY) }
+        INVGPU_ONESWEEP_ALL(INVGPU_ONESWEEP_TRY)
+    }
     INVGPU_TILE_SPD_ALL(INVGPU_TILE_TRY)
     return INVGPU_NO_FAST_PATH;
 }

@@ -64,3 +64,8 @@
 #define INVGPU_ONESWEEP_F32(X) X(float, 8, 1, 1, true, 4) X(float, 16, 2, 2, false, 4) X(float, 32, INVGPU_OS_F32_N32_TR, INVGPU_OS_F32_N32_TC, false, INVGPU_OS_F32_N32_MINB)
 #define INVGPU_ONESWEEP_F64(X) X(double, 8, 1, 1, true, 2) X(double, 16, 2, 2, false, 2) X(double, 32, 4, 4, false, 2)
 #define INVGPU_ONESWEEP_ALL(X) INVGPU_ONESWEEP_F32(X) INVGPU_ONESWEEP_F64(X)
+
+// SPD inverse, one-sweep ROLLED kernel for square thread grids (any group size):  X(T, N, P, MINB)
+#define INVGPU_OSR_F32(X) X(float, 32, 4, 5) X(float, 64, 8, 8) X(float, 128, 16, 2)
+#define INVGPU_OSR_F64(X) X(double, 64, 8, 4) X(double, 128, 16, 1)
+#define INVGPU_OSR_ALL(X) INVGPU_OSR_F32(X) INVGPU_OSR_F64(X)

@@ -11,6 +11,9 @@
 #include "tile_launch.cuh"
 
 #define INVGPU_NO_FAST_PATH (-1000)
+#ifndef INVGPU_SWEEP_MIN_N
+#define INVGPU_SWEEP_MIN_N 16
+#endif
 
 namespace invgpu {
 
@@ -31,9 +34,9 @@ static bool dense_aligned(const StridedIO<T> &io, int n) {
     if (std::is_same<T, TT>::value && n == N)                                                        \
         return launch_onesweep<TT, N, TR, TC, STAGE, MINB>(*reinterpret_cast<StridedIO<TT> *>(&io), batch, dInfo, st, ds);
 
-#define INVGPU_OSR_TRY(TT, N, P, MINB)                                                              \
-    if (std::is_same<T, TT>::value && n == N)                                                        \
-        return launch_onesweep_rolled<TT, N, P, MINB>(*reinterpret_cast<StridedIO<TT> *>(&io), batch, dInfo, st, ds);
+#define INVGPU_SWEEP_TRY(V, TT, N, TR, TC, UNROLL, MINB)                                            \
+    if (std::is_same<T, TT>::value && n == N && V == variant)                                        \
+        return launch_sweep<TT, N, TR, TC, UNROLL, MINB>(*reinterpret_cast<StridedIO<TT> *>(&io), batch, dInfo, st, ds);
 
 // INVGPU_SPD_KERNEL=threesweep selects the three-sweep tile kernels for the sizes both families cover
 static bool prefer_onesweep() {
@@ -46,12 +49,16 @@ template <typename T, int STAGES>
 static int fast_spd_dense(StridedIO<T> io, int n, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds) {
     if (!dense_aligned(io, n)) return INVGPU_NO_FAST_PATH;
     if (STAGES == SPD_INVERSE && prefer_onesweep()) {
-        // n >= 64: the rolled sweep kernel (sweep_kernels.cuh); n <= 32: the fully unrolled one-sweep kernel.
-        // INVGPU_SPD_KERNEL=rolled prefers the rolled kernel wherever it is instantiated (experiments).
-        static int rolled = -1;
-        if (rolled < 0) { const char *e = getenv("INVGPU_SPD_KERNEL"); rolled = (e && !strcmp(e, "rolled")) ? 1 : 0; }
-        if (rolled || n >= 64) { INVGPU_OSR_ALL(INVGPU_OSR_TRY) }
+        // n >= INVGPU_SWEEP_MIN_N: the look-ahead sweep kernel (sweep_kernels.cuh); below: the unrolled one-sweep
+        // kernel.  INVGPU_SWEEP_VARIANT=V picks another instantiated thread grid, INVGPU_SPD_KERNEL=onesweep
+        // keeps the older kernel for every size it covers (experiments, tools/kbench.py).
+        static int env_variant = -1, old = -1;
+        if (env_variant < 0) { const char *e = getenv("INVGPU_SWEEP_VARIANT"); env_variant = e ? atoi(e) : 0; }
+        int variant = env_variant;
+        if (old < 0) { const char *e = getenv("INVGPU_SPD_KERNEL"); old = (e && !strcmp(e, "onesweep")) ? 1 : 0; }
+        if (!old && n >= INVGPU_SWEEP_MIN_N) { INVGPU_SWEEP_ALL(INVGPU_SWEEP_TRY) }
         INVGPU_ONESWEEP_ALL(INVGPU_ONESWEEP_TRY)
+        if (!old) { variant = 0; INVGPU_SWEEP_ALL(INVGPU_SWEEP_TRY) }
     }
     INVGPU_TILE_SPD_ALL(INVGPU_TILE_TRY)
     return INVGPU_NO_FAST_PATH;

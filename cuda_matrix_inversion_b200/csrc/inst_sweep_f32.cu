@@ -1,4 +1,4 @@
 #define INVGPU_TILE_DEFINE
 #include "tile_launch.cuh"
 #include "tile_configs.h"
-INVGPU_OSR_F64(INVGPU_ONESWEEP_ROLLED_INSTANTIATE)
+INVGPU_SWEEP_F32(INVGPU_SWEEP_INSTANTIATE)

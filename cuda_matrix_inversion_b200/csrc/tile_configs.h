@@ -65,7 +65,14 @@
 #define INVGPU_ONESWEEP_F64(X) X(double, 8, 1, 1, true, 2) X(double, 16, 2, 2, false, 2) X(double, 32, 4, 4, false, 2)
 #define INVGPU_ONESWEEP_ALL(X) INVGPU_ONESWEEP_F32(X) INVGPU_ONESWEEP_F64(X)
 
-// SPD inverse, one-sweep ROLLED kernel for square thread grids (any group size):  X(T, N, P, MINB)
-#define INVGPU_OSR_F32(X) X(float, 32, 4, 5) X(float, 64, 8, 8) X(float, 128, 16, 2)
-#define INVGPU_OSR_F64(X) X(double, 64, 8, 4) X(double, 128, 16, 1)
-#define INVGPU_OSR_ALL(X) INVGPU_OSR_F32(X) INVGPU_OSR_F64(X)
+// SPD inverse, look-ahead sweep kernel (sweep_kernels.cuh):  X(V, T, N, TR, TC, UNROLL, MINB)
+// V = variant number; V == 0 is what the dispatcher uses, the others are reachable with
+// INVGPU_SWEEP_VARIANT=V (tools/kbench.py experiments).
+#define INVGPU_SWEEP_F32(X)                                                                     \
+    X(0, float, 16, 2, 2, false, 4) X(1, float, 16, 1, 2, false, 3)                             \
+    X(0, float, 32, 2, 4, false, 3) X(1, float, 32, 4, 2, false, 3) X(2, float, 32, 4, 4, false, 5) X(3, float, 32, 2, 4, true, 3) \
+    X(0, float, 64, 4, 8, false, 3) X(1, float, 64, 8, 8, false, 8)                             \
+    X(0, float, 128, 8, 16, false, 3) X(1, float, 128, 16, 16, false, 2)
+#define INVGPU_SWEEP_F64(X)                                                                     \
+    X(0, double, 16, 2, 2, false, 2) X(0, double, 32, 4, 4, false, 2) X(0, double, 64, 8, 8, false, 4) X(0, double, 128, 16, 16, false, 1)
+#define INVGPU_SWEEP_ALL(X) INVGPU_SWEEP_F32(X) INVGPU_SWEEP_F64(X)

@@ -19,8 +19,8 @@ int launch_gj(IO io, int n, i64 batch, int *dInfo, cudaStream_t st, DeviceState 
 template <typename T, int N, int TR, int TC, bool STAGE, int MINB>
 int launch_onesweep(StridedIO<T> io, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds);
 
-template <typename T, int N, int P, int MINB>
-int launch_onesweep_rolled(StridedIO<T> io, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds);
+template <typename T, int N, int TR, int TC, bool UNROLL, int MINB>
+int launch_sweep(StridedIO<T> io, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds);
 
 }  // namespace invgpu
 
@@ -32,15 +32,15 @@ int launch_onesweep_rolled(StridedIO<T> io, i64 batch, int *dInfo, cudaStream_t 
 
 namespace invgpu {
 
-template <typename T, int N, int P, int MINB>
-int launch_onesweep_rolled(StridedIO<T> io, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds) {
-    using G = TileGeo<N, P, P, false>;
-    auto kern = sweep_rolled_kernel<T, N, P, StridedIO<T>, MINB>;
-    const size_t smem = (size_t)G::MPB * SweepGeo<N, P>::WORDS * sizeof(T);
+template <typename T, int N, int TR, int TC, bool UNROLL, int MINB>
+int launch_sweep(StridedIO<T> io, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds) {
+    using SG = SweepGeo<N, TR, TC>;
+    auto kern = sweep_spd_kernel<T, N, TR, TC, UNROLL, StridedIO<T>, MINB>;
+    const size_t smem = (size_t)SG::MPB * SG::WORDS * sizeof(T);
     int grid = 0;
-    int rc = persistent_grid(kern, G::BLOCK, smem, (batch + G::MPB - 1) / G::MPB, ds, &grid);
+    int rc = persistent_grid(kern, SG::BLOCK, smem, (batch + SG::MPB - 1) / SG::MPB, ds, &grid);
     if (rc) return rc;
-    kern<<<grid, G::BLOCK, smem, st>>>(io, batch, dInfo);
+    kern<<<grid, SG::BLOCK, smem, st>>>(io, batch, dInfo);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return (int)cudaGetLastError();
 }
@@ -120,8 +120,8 @@ int launch_tile_gp(GpIO<T> io, i64 batch, int *dInfo, cudaStream_t st, DeviceSta
     template int invgpu::launch_gj<T, N, ROWS, invgpu::PtrIO<T>, MINB>(invgpu::PtrIO<T>, int, invgpu::i64, int *, cudaStream_t, invgpu::DeviceState *);
 #define INVGPU_ONESWEEP_INSTANTIATE(T, N, TR, TC, STAGE, MINB) \
     template int invgpu::launch_onesweep<T, N, TR, TC, STAGE, MINB>(invgpu::StridedIO<T>, invgpu::i64, int *, cudaStream_t, invgpu::DeviceState *);
-#define INVGPU_ONESWEEP_ROLLED_INSTANTIATE(T, N, P, MINB) \
-    template int invgpu::launch_onesweep_rolled<T, N, P, MINB>(invgpu::StridedIO<T>, invgpu::i64, int *, cudaStream_t, invgpu::DeviceState *);
+#define INVGPU_SWEEP_INSTANTIATE(V, T, N, TR, TC, UNROLL, MINB) \
+    template int invgpu::launch_sweep<T, N, TR, TC, UNROLL, MINB>(invgpu::StridedIO<T>, invgpu::i64, int *, cudaStream_t, invgpu::DeviceState *);
 #define INVGPU_TILE_INSTANTIATE_GP(T, N, TR, TC, MINB) \
     template int invgpu::launch_tile_gp<T, N, TR, TC, MINB>(invgpu::GpIO<T>, invgpu::i64, int *, cudaStream_t, invgpu::DeviceState *);
 #endif

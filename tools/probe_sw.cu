@@ -1,4 +1,4 @@
-// compile-only probe for the rolled sweep kernel
+// compile-only probe for the sweep kernel
 #include "../cuda_matrix_inversion_b200/csrc/generic_smem.cuh"
 #include "../cuda_matrix_inversion_b200/csrc/sweep_kernels.cuh"
 using namespace invgpu;
@@ -6,17 +6,18 @@ using namespace invgpu;
 #define PT float
 #endif
 #ifndef PN
-#define PN 128
+#define PN 32
 #endif
-#ifndef PP
-#define PP 16
+#ifndef PTR
+#define PTR 4
+#endif
+#ifndef PTC
+#define PTC 2
+#endif
+#ifndef PUNROLL
+#define PUNROLL false
 #endif
 #ifndef PMINB
-#define PMINB 2
+#define PMINB 3
 #endif
-#ifndef PUNROLLED
-template __global__ void invgpu::sweep_rolled_kernel<PT, PN, PP, StridedIO<PT>, PMINB>(StridedIO<PT>, i64, int *);
-#endif
-#ifdef PUNROLLED
-template __global__ void invgpu::sweep_unrolled_kernel<PT, 32, 4, 4, StridedIO<PT>, 5>(StridedIO<PT>, i64, int *);
-#endif
+template __global__ void invgpu::sweep_spd_kernel<PT, PN, PTR, PTC, PUNROLL, StridedIO<PT>, PMINB>(StridedIO<PT>, i64, int *);

@@ -7,6 +7,7 @@
 #include "generic_smem.cuh"
 #include "fast_tiers.cuh"
 #include "mixed_kernels.cuh"
+#include <chrono>
 #include <algorithm>
 
 #include "../../include/invgpu.h"
@@ -158,6 +159,7 @@ static int ensure_pipeline(DeviceState *ds, size_t slot_bytes) {
             INVGPU_TRY(cudaEventCreateWithFlags(&ds->ev_comp[i], cudaEventDisableTiming));
             INVGPU_TRY(cudaEventCreateWithFlags(&ds->ev_out[i], cudaEventDisableTiming));
         }
+        for (int i = 0; i < 5; ++i) INVGPU_TRY(cudaEventCreateWithFlags(&ds->ev_mixed[i], cudaEventDisableTiming));
         ds->streams_ready = true;
     }
     if (ds->d_ws_bytes < slot_bytes) {
@@ -336,24 +338,37 @@ static int run_mixed_spd(T *const *hIn, T *const *hOut, const int *hN, i64 count
     int err = 0;
     DeviceState *ds = device_state(&err);
     if (!ds) return err;
-    std::vector<MixedItem> bucket[3];
-    int nmax[3] = {1, 1, 1};
+    // INVGPU_MIXED_TIMING=1: print the host planning time and the per-bucket kernel times (diagnostics)
+    static int timing = -1;
+    if (timing < 0) { const char *e = getenv("INVGPU_MIXED_TIMING"); timing = (e && atoi(e) > 0) ? 1 : 0; }
+    const auto t_plan0 = std::chrono::steady_clock::now();
+    // counting sort by n, descending inside each bucket (longest work first): two passes, no comparisons
+    i64 hist[257];
+    memset(hist, 0, sizeof(hist));
     for (i64 i = 0; i < count; ++i) {
         const int n = hN[i];
         if (n < 1) return INVGPU_EARG;
         if (n > 256) return INVGPU_EUNSUPPORTED;
-        const int b = n <= 32 ? 0 : (n <= 128 ? 1 : 2);
-        MixedItem it; it.in = hIn[i]; it.out = hOut[i]; it.n = n; it.index = (int)i;
-        bucket[b].push_back(it);
-        if (n > nmax[b]) nmax[b] = n;
+        ++hist[n];
     }
-    for (int b = 0; b < 3; ++b)                               // longest work first
-        std::stable_sort(bucket[b].begin(), bucket[b].end(), [](const MixedItem &x, const MixedItem &y) { return x.n > y.n; });
-
+    // tier b holds n in (lo_b, hi_b]; position of the first item of order n in the concatenated list
+    constexpr int NT = 5;
+    static const int hi[NT] = {16, 32, 64, 128, 256}, lo[NT] = {0, 16, 32, 64, 128};
+    i64 bcount[NT] = {0, 0, 0, 0, 0}, first[257];
+    int nmax[NT] = {1, 1, 1, 1, 1};
+    {
+        i64 pos = 0;
+        for (int b = 0; b < NT; ++b)
+            for (int n = hi[b]; n > lo[b]; --n) {
+                first[n] = pos; pos += hist[n]; bcount[b] += hist[n];
+                if (hist[n] && n > nmax[b]) nmax[b] = n;
+            }
+    }
     std::lock_guard<std::mutex> lk(engine_mutex());
     int rc = ensure_pipeline(ds, 0);                          // streams + events
     if (rc) return rc;
-    const size_t need = (size_t)count * sizeof(MixedItem) + 64;
+    constexpr size_t HDR = 128;                               // tickets of the generic kernels
+    const size_t need = (size_t)count * sizeof(MixedItem) + HDR;
     if (ds->mixed_bytes < need) {
         if (ds->d_mixed) cudaFree(ds->d_mixed);
         if (ds->h_mixed) cudaFreeHost(ds->h_mixed);
@@ -365,29 +380,54 @@ static int run_mixed_spd(T *const *hIn, T *const *hOut, const int *hN, i64 count
     // the staging buffer is reused: wait for the previous call's upload
     INVGPU_TRY(cudaEventSynchronize(ds->ev_in[0]));
     char *h = (char *)ds->h_mixed;
-    memset(h, 0, 64);                                         // three tickets
-    size_t off = 64;
-    size_t start[3];
-    for (int b = 0; b < 3; ++b) {
-        start[b] = off;
-        memcpy(h + off, bucket[b].data(), bucket[b].size() * sizeof(MixedItem));
-        off += bucket[b].size() * sizeof(MixedItem);
+    memset(h, 0, HDR);
+    MixedItem *items = (MixedItem *)(h + HDR);
+    for (i64 i = 0; i < count; ++i) {                         // scatter straight into the pinned staging buffer
+        MixedItem &it = items[first[hN[i]]++];
+        it.in = hIn[i]; it.out = hOut[i]; it.n = hN[i]; it.index = (int)i;
     }
+    size_t start[NT];
+    size_t off = HDR;
+    for (int b = 0; b < NT; ++b) { start[b] = off; off += (size_t)bcount[b] * sizeof(MixedItem); }
+    const auto t_plan1 = std::chrono::steady_clock::now();
     INVGPU_TRY(cudaMemcpyAsync(ds->d_mixed, h, off, cudaMemcpyHostToDevice, st));
     INVGPU_TRY(cudaEventRecord(ds->ev_in[0], st));
+    // Tiers run concurrently on the engine's three streams (big matrices first).  Each tier is one persistent
+    // grid: the padded sweep kernel (every item of a tier costs the same, so its grid-stride work split is
+    // balanced by construction) or, where no padded tier exists (fp64 above 128), the any-n shared-memory
+    // kernel pulling work with an atomic ticket.  INVGPU_MIXED_KERNEL=generic forces the latter everywhere.
+    static int generic_only = -1;
+    if (generic_only < 0) { const char *e = getenv("INVGPU_MIXED_KERNEL"); generic_only = (e && !strcmp(e, "generic")) ? 1 : 0; }
     cudaStream_t lanes[3] = {ds->s_in, ds->s_comp, ds->s_out};
     char *d = (char *)ds->d_mixed;
-    for (int b = 2; b >= 0; --b) {                            // big matrices first
-        INVGPU_TRY(cudaStreamWaitEvent(lanes[b], ds->ev_in[0], 0));
+    for (int b = NT - 1; b >= 0; --b) {
+        if (bcount[b] == 0) continue;
+        cudaStream_t lane = lanes[b % 3];
+        INVGPU_TRY(cudaStreamWaitEvent(lane, ds->ev_in[0], 0));
         const MixedItem *di = (const MixedItem *)(d + start[b]);
         unsigned long long *tk = (unsigned long long *)(d + 16 * b);
-        if (b == 0) rc = launch_mixed_bucket<T, 32>(di, (i64)bucket[b].size(), nmax[b], dInfo, tk, lanes[b], ds);
-        else if (b == 1) rc = launch_mixed_bucket<T, 128>(di, (i64)bucket[b].size(), nmax[b], dInfo, tk, lanes[b], ds);
-        else rc = launch_mixed_bucket<T, 256>(di, (i64)bucket[b].size(), nmax[b], dInfo, tk, lanes[b], ds);
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        if (timing) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, lane); }
+        rc = INVGPU_NO_FAST_PATH;
+        if (!generic_only) { PadIO<T> pio; pio.items = di; rc = fast_padded<T>(pio, hi[b], bcount[b], dInfo, lane, ds); }
+        if (rc == INVGPU_NO_FAST_PATH) {
+            if (hi[b] <= 32) rc = launch_mixed_bucket<T, 32>(di, bcount[b], nmax[b], dInfo, tk, lane, ds);
+            else if (hi[b] <= 128) rc = launch_mixed_bucket<T, 128>(di, bcount[b], nmax[b], dInfo, tk, lane, ds);
+            else rc = launch_mixed_bucket<T, 256>(di, bcount[b], nmax[b], dInfo, tk, lane, ds);
+        }
         if (rc) return rc;
-        INVGPU_TRY(cudaEventRecord(ds->ev_comp[b], lanes[b]));
-        INVGPU_TRY(cudaStreamWaitEvent(st, ds->ev_comp[b], 0));
+        if (timing) {                                          // serialises the tiers: diagnostics only
+            cudaEventRecord(e1, lane); cudaEventSynchronize(e1);
+            float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+            fprintf(stderr, "[invgpu mixed] tier <=%d: %lld matrices, nmax %d, %.3f ms\n", hi[b], (long long)bcount[b], nmax[b], ms);
+            cudaEventDestroy(e0); cudaEventDestroy(e1);
+        }
+        INVGPU_TRY(cudaEventRecord(ds->ev_mixed[b], lane));
+        INVGPU_TRY(cudaStreamWaitEvent(st, ds->ev_mixed[b], 0));
     }
+    if (timing)
+        fprintf(stderr, "[invgpu mixed] host planning %.3f ms for %lld matrices\n",
+                std::chrono::duration<double, std::milli>(t_plan1 - t_plan0).count(), (long long)count);
     return 0;
 }
 

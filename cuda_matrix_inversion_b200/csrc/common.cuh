@@ -33,6 +33,23 @@ struct PtrIO {
     __device__ __forceinline__ T *dst(i64 k) const { return out[k]; }
 };
 
+// Mixed-dimension batches: one work item per matrix (device pointers, column-major n x n, lda = n).
+struct MixedItem {
+    const void *in;
+    void *out;
+    int n;
+    int index;          // position in the caller's arrays (for info[])
+};
+// IO policy of the padded tiers: matrix k of order n <= N is embedded as blockdiag(A, I) in the N x N
+// register tile of a fixed-order kernel ((A (+) I)^-1 = A^-1 (+) I; the identity part costs nothing but
+// the FMAs of its pivots); loads / stores are bounds-checked scalar accesses (lda = n: no alignment).
+template <typename T>
+struct PadIO {
+    const MixedItem *items;
+};
+template <typename IO> struct IoTraits { static constexpr bool PADDED = false; };
+template <typename T> struct IoTraits<PadIO<T>> { static constexpr bool PADDED = true; };
+
 // Inputs of the fused GP kernels (reference include/gauss_cpu.h:16-58): dense, contiguous.
 template <typename T>
 struct GpIO {

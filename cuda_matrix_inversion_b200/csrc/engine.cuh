@@ -36,6 +36,7 @@ struct DeviceState {
     size_t h_ring_bytes = 0;
     cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
     cudaEvent_t ev_in[kSlots], ev_comp[kSlots], ev_out[kSlots];
+    cudaEvent_t ev_mixed[5];                                  // one per tier of the mixed-dimension scheduler
     bool streams_ready = false;
     // scratch of the fused GP tile kernels (natural-order info recomputation of flagged matrices)
     void *gp_scratch = nullptr;

@@ -100,11 +100,29 @@ static int fast_general(IO io, int n, i64 batch, int *dInfo, cudaStream_t st, De
     if (std::is_same<T, TT>::value && n == N)                                                        \
         return launch_tile_gp<TT, N, TR, TC, MINB>(*reinterpret_cast<GpIO<TT> *>(&io), batch, dInfo, st, ds);
 
+#define INVGPU_SWEEP_TRY_GP(TT, N, TR, TC, UNROLL, MINB)                                            \
+    if (std::is_same<T, TT>::value && n == N)                                                        \
+        return launch_sweep_gp<TT, N, TR, TC, UNROLL, MINB>(*reinterpret_cast<GpIO<TT> *>(&io), batch, dInfo, st, ds);
+
 template <typename T>
 static int fast_gp(GpIO<T> io, int n, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds) {
     const uintptr_t all = (uintptr_t)io.a | (uintptr_t)io.b | (uintptr_t)io.c | (uintptr_t)io.d;
     if (all % 16 != 0 || ((size_t)n * sizeof(T)) % 16 != 0) return INVGPU_NO_FAST_PATH;
+    static int old = -1;                              // INVGPU_GP_KERNEL=tile keeps the three-phase tile kernels
+    if (old < 0) { const char *e = getenv("INVGPU_GP_KERNEL"); old = (e && !strcmp(e, "tile")) ? 1 : 0; }
+    if (!old) { INVGPU_SWEEP_GP_ALL(INVGPU_SWEEP_TRY_GP) }
     INVGPU_TILE_GP_ALL(INVGPU_TILE_TRY_GP)
+    return INVGPU_NO_FAST_PATH;
+}
+
+// mixed-dimension batches: the padded sweep tier of order exactly N, if instantiated for T
+#define INVGPU_SWEEP_PAD_TRY(TT, N, TR, TC, MINB)                                                   \
+    if (std::is_same<T, TT>::value && tier_n == N)                                                   \
+        return launch_sweep_pad<TT, N, TR, TC, MINB>(*reinterpret_cast<PadIO<TT> *>(&io), batch, dInfo, st, ds);
+
+template <typename T>
+static int fast_padded(PadIO<T> io, int tier_n, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds) {
+    INVGPU_SWEEP_PAD_ALL(INVGPU_SWEEP_PAD_TRY)
     return INVGPU_NO_FAST_PATH;
 }
 

@@ -14,13 +14,6 @@
 
 namespace invgpu {
 
-struct MixedItem {
-    const void *in;     // device pointer, column-major n x n, lda = n
-    void *out;          // device pointer
-    int n;
-    int index;          // position in the caller's arrays (for info[])
-};
-
 // G = 32: one matrix per warp, 8 warps per CTA; G = 128 / 256: one matrix per CTA.
 template <typename T, int G>
 __global__ void __launch_bounds__(G <= 32 ? 256 : G)

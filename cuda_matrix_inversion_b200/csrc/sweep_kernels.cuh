@@ -35,6 +35,17 @@
 
 #include "tile_kernels.cuh"
 
+// Measured on B200 (tools/variant.sh A/B/C, n = 16 / 32 fp32): interleaving the lanes of the matrices that
+// share a warp (column owners in one quarter-warp: fewer shared-memory store wavefronts) costs 15-17 %
+// because the global loads / stores lose their 32-byte runs; re-aligning the warps of a CTA for
+// instruction-cache sharing is neutral (n = 32) to negative (n = 16).  Both stay off.
+#ifndef INVGPU_SWEEP_INTERLEAVE
+#define INVGPU_SWEEP_INTERLEAVE 0
+#endif
+#ifndef INVGPU_SWEEP_LOCKSTEP
+#define INVGPU_SWEEP_LOCKSTEP 0
+#endif
+
 namespace invgpu {
 
 // two vertically adjacent tile elements (rows 2i, 2i+1 of one column)
@@ -86,6 +97,8 @@ __device__ __forceinline__ void sts_one(double *p, double v) {
     asm volatile("st.shared.f64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(p)), "d"(v) : "memory");
 }
 
+enum { SWEEP_INVERSE = 0, SWEEP_GP = 1 };
+
 template <int N, int TR, int TC>
 struct SweepGeo {
     static constexpr int SR = N / TR, SC = N / TC;                 // register tile
@@ -93,31 +106,52 @@ struct SweepGeo {
     static constexpr int NGR = SR / 4, NGC = SC / 4;               // 4-groups per thread
     static constexpr int LANES = TR * TC;
     static constexpr int PMIN = TR < TC ? TR : TC;
+    static constexpr int PMAX = TR < TC ? TC : TR;
     static constexpr int NB = N / 4;                               // 4-blocks per side
-    static constexpr int NR = NB / PMIN;                           // ranges of PMIN consecutive blocks
+    static constexpr int NS = NB / PMAX;                           // super-ranges of PMAX consecutive blocks
+    static constexpr int SUBS = PMAX / PMIN;                       // ranges of PMIN blocks per super-range
+    static constexpr int RG = PMAX / TR, CG = PMAX / TC;           // register groups per super-range
     static_assert(N % (4 * TR) == 0 && N % (4 * TC) == 0, "N must be a multiple of 4 TR and 4 TC");
-    static_assert(TR % PMIN == 0 && TC % PMIN == 0, "TR and TC must divide each other");
-    static constexpr int LINE = N + 4;                             // z line + the pivot word (16-byte aligned)
+    static_assert(PMAX % PMIN == 0, "TR and TC must divide each other");
+    static constexpr int LINE = N + 4;                             // z line + pivot word + two right-hand-side words
     static constexpr int WORDS = ((2 * LINE + 31) / 32) * 32 + (LANES < 32 ? 8 : 0);
     static constexpr int BLOCK = LANES >= 64 ? LANES : INVGPU_WARP_TIER_BLOCK;
     static constexpr int MPB = BLOCK / LANES;
     // no thread holds a lower-triangle element in (row pair i, column c)
     __host__ __device__ static constexpr bool upper(int i, int c) { return TR * ((2 * i) / 4) + TR - 1 < TC * (c / 4); }
+    // Pivot order: for S (super-range), for W (index within the 4-block), for SUB, for t:
+    //   block q = S PMAX + SUB PMIN + t,  pivot 4 q + W.
+    // After level (S, W) every thread has eliminated its row / column slots (g, W), g in super-range S:
+    // for the factor-only (GP) mode rows and columns die evenly over the threads and are pruned statically.
+    __host__ __device__ static constexpr bool row_dead(int slot, int S, int W) {
+        return (slot / 4) / RG < S || ((slot / 4) / RG == S && slot % 4 < W);
+    }
+    __host__ __device__ static constexpr bool col_dead(int slot, int S, int W) {
+        return (slot / 4) / CG < S || ((slot / 4) / CG == S && slot % 4 < W);
+    }
+    template <int MODE>
+    __host__ __device__ static constexpr bool skip(int i, int c, int S, int W) {
+        return upper(i, c) || (MODE == SWEEP_GP && (row_dead(2 * i + 1, S, W) || col_dead(c, S, W)));
+    }
+    // right-hand sides of the GP mode: combination cb = e H + ip (vector e, row pair ip) lives in lane cb % TC
+    static constexpr int NC = (2 * H + TC - 1) / TC;
 };
 
-// element `odd` of a pair: read it and zero it
-template <typename T, typename PR>
+// element `odd` of a pair: read it and (inverse mode) zero it
+template <typename T, int MODE, typename PR>
 __device__ __forceinline__ T pair_take(PR &p, bool odd) {
     T e;
-    if (!odd) { e = p.lo(); p = PR::make(T(0), p.hi()); }
-    else { e = p.hi(); p = PR::make(p.lo(), T(0)); }
+    if (!odd) { e = p.lo(); if (MODE == SWEEP_INVERSE) p = PR::make(T(0), p.hi()); }
+    else { e = p.hi(); if (MODE == SWEEP_INVERSE) p = PR::make(p.lo(), T(0)); }
     return e;
 }
 
-// Publish pivot k' = 4 qn + WN (block qn = TR GRN + rkn = TC HCN + ckn) into line zn, raw, and restart
-// the published slots:  zn[i] = T_ik' (i != k'),  zn[k'] = -1,  zn[N] = T_k'k' = -d.
-template <typename T, int N, int TR, int TC, int GRN, int HCN, int WN>
-__device__ __forceinline__ void sweep_publish(Pair2<T> (&ap)[N / TR / 2][N / TC], T *zn, int ti, int tj, int qn) {
+// Publish pivot k' = 4 qn + WN (block qn = TR GRN + rkn = TC HCN + ckn) into line zn, raw, and (inverse
+// mode) restart the published slots:  zn[i] = T_ik' (i != k'),  zn[k'] = -1,  zn[N] = T_k'k' = -d;
+// GP mode: zn[N+1], zn[N+2] = the two right-hand sides at row k'.
+template <typename T, int N, int TR, int TC, int MODE, int GRN, int HCN, int WN>
+__device__ __forceinline__ void sweep_publish(Pair2<T> (&ap)[N / TR / 2][N / TC], Pair2<T> (&rhs)[SweepGeo<N, TR, TC>::NC],
+                                              T *zn, int ti, int tj, int qn) {
     using SG = SweepGeo<N, TR, TC>;
     using PR = Pair2<T>;
     constexpr int srn = 4 * GRN + WN, scn = 4 * HCN + WN, ipn = srn / 2;
@@ -128,8 +162,7 @@ __device__ __forceinline__ void sweep_publish(Pair2<T> (&ap)[N / TR / 2][N / TC]
             if (g > GRN || ti > rkn) {
                 sts_pair(zn + 4 * (TR * g + ti), ap[2 * g][scn]);
                 sts_pair(zn + 4 * (TR * g + ti) + 2, ap[2 * g + 1][scn]);
-                ap[2 * g][scn].clear();
-                ap[2 * g + 1][scn].clear();
+                if (MODE == SWEEP_INVERSE) { ap[2 * g][scn].clear(); ap[2 * g + 1][scn].clear(); }
             }
         }
     }
@@ -138,30 +171,39 @@ __device__ __forceinline__ void sweep_publish(Pair2<T> (&ap)[N / TR / 2][N / TC]
         for (int h = 0; h <= HCN; ++h) {
             if (h < HCN || tj < ckn) {
                 #pragma unroll
-                for (int v = 0; v < 4; ++v)                        // scalar stores: no register-quad staging
-                    sts_one(zn + 4 * (TC * h + tj) + v, pair_take<T>(ap[ipn][4 * h + v], srn % 2));
+                for (int v = 0; v < 4; ++v)
+                    sts_one(zn + 4 * (TC * h + tj) + v, pair_take<T, MODE>(ap[ipn][4 * h + v], srn % 2));
             }
         }
         if (tj == ckn) {                                           // diagonal thread: block qn = [row part | -1 | column part]
             T e[4];
             #pragma unroll
             for (int v = 0; v < 4; ++v) {
-                if (v <= WN) e[v] = pair_take<T>(ap[ipn][4 * HCN + v], srn % 2);
-                else e[v] = pair_take<T>(ap[(4 * GRN + v) / 2][scn], (4 * GRN + v) % 2);
+                if (v <= WN) e[v] = pair_take<T, MODE>(ap[ipn][4 * HCN + v], srn % 2);
+                else e[v] = pair_take<T, MODE>(ap[(4 * GRN + v) / 2][scn], (4 * GRN + v) % 2);
             }
             sts_one(zn + N, e[WN]);
             e[WN] = T(-1);
             #pragma unroll
             for (int v = 0; v < 4; ++v) sts_one(zn + 4 * qn + v, e[v]);
         }
+        if (MODE == SWEEP_GP) {                                    // the lanes holding row k' of the right-hand sides
+            #pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                constexpr int dummy = 0; (void)dummy;
+                const int cb = e * SG::H + ipn;                    // static
+                if (tj == cb % TC) sts_one(zn + N + 1 + e, (srn % 2) ? rhs[cb / TC].hi() : rhs[cb / TC].lo());
+            }
+        }
     }
 }
 
 // One pivot whose line zc is published and visible: load its operands, bring the slots of the NEXT
 // pivot up to date and publish them into zn, barrier, then the bulk of the rank-1 update.
-template <typename T, int N, int TR, int TC, int GRN, int HCN, int WN, bool HAS_NEXT>
-__device__ __forceinline__ void sweep_step(Pair2<T> (&ap)[N / TR / 2][N / TC], const T *zc, T *zn, int ti, int tj, int qn,
-                                           T &dmin, T &d) {
+// (S, W): elimination level of THIS pivot (static pruning in GP mode).
+template <typename T, int N, int TR, int TC, int MODE, int S, int W, int GRN, int HCN, int WN, bool HAS_NEXT>
+__device__ __forceinline__ void sweep_step(Pair2<T> (&ap)[N / TR / 2][N / TC], Pair2<T> (&rhs)[SweepGeo<N, TR, TC>::NC],
+                                           const T *zc, T *zn, int ti, int tj, int qn, T &dmin, T &d, T &acc_m, T &acc_q) {
     using SG = SweepGeo<N, TR, TC>;
     using PR = Pair2<T>;
     constexpr int srn = 4 * GRN + WN, scn = 4 * HCN + WN, ipn = srn / 2;
@@ -172,73 +214,127 @@ __device__ __forceinline__ void sweep_step(Pair2<T> (&ap)[N / TR / 2][N / TC], c
     T y[SG::SC];
     #pragma unroll
     for (int g = 0; g < SG::NGR; ++g) {
+        if (MODE == SWEEP_GP && SG::row_dead(4 * g + 3, S, W)) continue;     // the whole group is dead
         T x0, x1, x2, x3;
         ld4(zc + 4 * (TR * g + ti), x0, x1, x2, x3);
         x[2 * g] = PR::make(x0, x1); x[2 * g + 1] = PR::make(x2, x3);
         x[2 * g].scale(r); x[2 * g + 1].scale(r);
     }
     #pragma unroll
-    for (int h = 0; h < SG::NGC; ++h)
+    for (int h = 0; h < SG::NGC; ++h) {
+        if (MODE == SWEEP_GP && SG::col_dead(4 * h + 3, S, W)) continue;
         ld4(zc + 4 * (TC * h + tj), y[4 * h], y[4 * h + 1], y[4 * h + 2], y[4 * h + 3]);
+    }
+    if (MODE == SWEEP_GP) {                                        // right-hand sides: u_i += x_i u_k, and the two scalars
+        const T uk = zc[N + 1], vk = zc[N + 2];
+        const T ur = uk * r;
+        acc_m = fma(ur, vk, acc_m);
+        acc_q = fma(ur, uk, acc_q);
+        #pragma unroll
+        for (int j = 0; j < SG::NC; ++j) {
+            const int cb = tj + TC * j;                            // vector cb / H, row pair cb % H of this thread's rows
+            const int ip = cb % SG::H;
+            const T *zp = zc + 4 * (TR * (ip / 2) + ti) + 2 * (ip % 2);
+            PR xs = PR::make(zp[0], zp[1]);
+            xs.scale(r);
+            rhs[j].fma_bcast(xs, cb / SG::H == 0 ? uk : vk);
+        }
+    }
     if (HAS_NEXT) {
         #pragma unroll
         for (int i = 0; i < SG::H; ++i)                            // column slot of the next pivot
-            if (!SG::upper(i, scn)) ap[i][scn].fma_bcast(x[i], y[scn]);
+            if (!SG::template skip<MODE>(i, scn, S, W)) ap[i][scn].fma_bcast(x[i], y[scn]);
         #pragma unroll
         for (int c = 0; c < SG::SC; ++c)                           // row pair of the next pivot
-            if (c != scn && !SG::upper(ipn, c)) ap[ipn][c].fma_bcast(x[ipn], y[c]);
-        sweep_publish<T, N, TR, TC, GRN, HCN, WN>(ap, zn, ti, tj, qn);
+            if (c != scn && !SG::template skip<MODE>(ipn, c, S, W)) ap[ipn][c].fma_bcast(x[ipn], y[c]);
+        sweep_publish<T, N, TR, TC, MODE, GRN, HCN, WN>(ap, rhs, zn, ti, tj, qn);
         tile_sync<SG::LANES>();
     }
     #pragma unroll
     for (int i = 0; i < SG::H; ++i)
         #pragma unroll
         for (int c = 0; c < SG::SC; ++c) {
-            if (SG::upper(i, c)) continue;
+            if (SG::template skip<MODE>(i, c, S, W)) continue;
             if (HAS_NEXT && (c == scn || i == ipn)) continue;      // done before the publish
             ap[i][c].fma_bcast(x[i], y[c]);
         }
 }
 
-// all pivots of range R, sub-index W
-template <typename T, int N, int TR, int TC, int R, int W, bool UNROLL>
-__device__ __forceinline__ void sweep_range(Pair2<T> (&ap)[N / TR / 2][N / TC], T *sm, int ti, int tj, T &dmin, T &d) {
+// all pivots of level (S, W), range SUB
+template <typename T, int N, int TR, int TC, int MODE, bool UNROLL, int S, int W, int SUB>
+__device__ __forceinline__ void sweep_range(Pair2<T> (&ap)[N / TR / 2][N / TC], Pair2<T> (&rhs)[SweepGeo<N, TR, TC>::NC],
+                                            T *sm, int ti, int tj, T &dmin, T &d, T &acc_m, T &acc_q) {
     using SG = SweepGeo<N, TR, TC>;
     constexpr int PM = SG::PMIN;
-    constexpr int GR = (R * PM) / TR, HC = (R * PM) / TC;
-    constexpr int J0 = (4 * R + W) * PM;                           // sequence number of the first pivot of this body
+    constexpr int Q0 = S * SG::PMAX + SUB * PM;                    // first block of this range
+    constexpr int GR = Q0 / TR, HC = Q0 / TC;
+    constexpr int J0 = ((4 * S + W) * SG::SUBS + SUB) * PM;        // sequence number of the first pivot of this body
+    // warp tiers: optionally re-align the warps of the CTA so that they share instruction fetches
+    if (SG::LANES <= 32 && INVGPU_SWEEP_LOCKSTEP > 0 && J0 % (INVGPU_SWEEP_LOCKSTEP > 0 ? INVGPU_SWEEP_LOCKSTEP : 1) == 0) __syncthreads();
     // t = 0 .. PM-2: the next pivot has the same static slots
     if (UNROLL) {
         #pragma unroll
         for (int t = 0; t < PM - 1; ++t) {
             const int par = (J0 + t) & 1;
-            sweep_step<T, N, TR, TC, GR, HC, W, true>(ap, sm + par * SG::LINE, sm + (par ^ 1) * SG::LINE, ti, tj, R * PM + t + 1, dmin, d);
+            sweep_step<T, N, TR, TC, MODE, S, W, GR, HC, W, true>(ap, rhs, sm + par * SG::LINE, sm + (par ^ 1) * SG::LINE, ti, tj,
+                                                                  Q0 + t + 1, dmin, d, acc_m, acc_q);
         }
     } else {
         #pragma unroll 1
         for (int t = 0; t < PM - 1; ++t) {
             const int par = (J0 + t) & 1;
-            sweep_step<T, N, TR, TC, GR, HC, W, true>(ap, sm + par * SG::LINE, sm + (par ^ 1) * SG::LINE, ti, tj, R * PM + t + 1, dmin, d);
+            sweep_step<T, N, TR, TC, MODE, S, W, GR, HC, W, true>(ap, rhs, sm + par * SG::LINE, sm + (par ^ 1) * SG::LINE, ti, tj,
+                                                                  Q0 + t + 1, dmin, d, acc_m, acc_q);
         }
     }
     // t = PM-1: the next pivot opens the next body
     constexpr int par = (J0 + PM - 1) & 1;
-    constexpr bool last = (R == SG::NR - 1) && (W == 3);
-    constexpr int RN = (W == 3) ? R + 1 : R, WN = (W == 3) ? 0 : W + 1;
-    constexpr int GRN = last ? 0 : (RN * PM) / TR, HCN = last ? 0 : (RN * PM) / TC;
-    sweep_step<T, N, TR, TC, GRN, HCN, WN, !last>(ap, sm + par * SG::LINE, sm + (par ^ 1) * SG::LINE, ti, tj, RN * PM, dmin, d);
+    constexpr bool last = (S == SG::NS - 1) && (W == 3) && (SUB == SG::SUBS - 1);
+    constexpr int SUBN = (SUB + 1 < SG::SUBS) ? SUB + 1 : 0;
+    constexpr int WN = (SUBN != 0) ? W : (W == 3 ? 0 : W + 1);
+    constexpr int SN = (SUBN != 0 || W != 3) ? S : S + 1;
+    constexpr int QN = last ? 0 : SN * SG::PMAX + SUBN * PM;
+    sweep_step<T, N, TR, TC, MODE, S, W, QN / TR, QN / TC, WN, !last>(ap, rhs, sm + par * SG::LINE, sm + (par ^ 1) * SG::LINE, ti, tj,
+                                                                     QN, dmin, d, acc_m, acc_q);
 }
 
-template <typename T, int N, int TR, int TC, bool UNROLL, int R>
+template <typename T, int N, int TR, int TC, int MODE, bool UNROLL, int S, int W, int SUB>
 struct SweepRanges {
-    static __device__ __forceinline__ void run(Pair2<T> (&ap)[N / TR / 2][N / TC], T *sm, int ti, int tj, T &dmin, T &d) {
-        sweep_range<T, N, TR, TC, R, 0, UNROLL>(ap, sm, ti, tj, dmin, d);
-        sweep_range<T, N, TR, TC, R, 1, UNROLL>(ap, sm, ti, tj, dmin, d);
-        sweep_range<T, N, TR, TC, R, 2, UNROLL>(ap, sm, ti, tj, dmin, d);
-        sweep_range<T, N, TR, TC, R, 3, UNROLL>(ap, sm, ti, tj, dmin, d);
-        if constexpr (R + 1 < SweepGeo<N, TR, TC>::NR) SweepRanges<T, N, TR, TC, UNROLL, R + 1>::run(ap, sm, ti, tj, dmin, d);
+    static __device__ __forceinline__ void run(Pair2<T> (&ap)[N / TR / 2][N / TC], Pair2<T> (&rhs)[SweepGeo<N, TR, TC>::NC],
+                                               T *sm, int ti, int tj, T &dmin, T &d, T &acc_m, T &acc_q) {
+        using SG = SweepGeo<N, TR, TC>;
+        sweep_range<T, N, TR, TC, MODE, UNROLL, S, W, SUB>(ap, rhs, sm, ti, tj, dmin, d, acc_m, acc_q);
+        constexpr int SUBN = (SUB + 1 < SG::SUBS) ? SUB + 1 : 0;
+        constexpr int WN = (SUBN != 0) ? W : (W == 3 ? 0 : W + 1);
+        constexpr int SN = (SUBN != 0 || W != 3) ? S : S + 1;
+        if constexpr (SN < SG::NS) SweepRanges<T, N, TR, TC, MODE, UNROLL, SN, WN, SUBN>::run(ap, rhs, sm, ti, tj, dmin, d, acc_m, acc_q);
     }
 };
+
+// Padded tiers (PadIO): the logical-lower positions of the tile from the UPPER triangle of a column-major
+// n x n matrix (lda = n, n <= N), identity outside; and the store of the leading n x n part of the result.
+template <typename T, int N, int TR, int TC>
+__device__ __forceinline__ void tile_load_upper_padded(T (&a)[N / TR][N / TC], const T *__restrict__ src, int n, int ti, int tj) {
+    using SG = SweepGeo<N, TR, TC>;
+    #pragma unroll
+    for (int g = 0; g < SG::NGR; ++g)
+        #pragma unroll
+        for (int h = 0; h < SG::NGC; ++h) {
+            const int br = TR * g + ti, bc = TC * h + tj;
+            #pragma unroll
+            for (int w = 0; w < 4; ++w)
+                #pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    const int r = 4 * br + w, c = 4 * bc + v;
+                    T e = T(0);
+                    if (!SG::upper(2 * g, 4 * h) && r >= c) {
+                        if (r < n) e = src[(size_t)r * n + c];      // element (row c, column r) of the upper triangle
+                        else if (r == c) e = T(1);
+                    }
+                    a[4 * g + w][4 * h + v] = e;
+                }
+        }
+}
 
 template <typename T, int N, int TR, int TC, bool UNROLL, typename IO, int MINB>
 __global__ void __launch_bounds__((SweepGeo<N, TR, TC>::BLOCK), MINB)
@@ -249,21 +345,42 @@ sweep_spd_kernel(IO io, i64 batch, int *__restrict__ info) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *smem = reinterpret_cast<T *>(smem_raw);
 
-    const int grp = threadIdx.x / SG::LANES;
-    const int lane = threadIdx.x % SG::LANES;
-    const int ti = lane / TC, tj = lane % TC;
+    // Lane map.  Groups smaller than a warp are INTERLEAVED: lane = ti + TR (mat + MPW tj), so that the
+    // owners of a pivot column (tj == const) of all the matrices of a warp sit in one quarter-warp and
+    // their 128-bit stores cost one shared-memory wavefront instead of four.
+    int grp, ti, tj;
+    if (SG::LANES < 32 && INVGPU_SWEEP_INTERLEAVE) {
+        constexpr int MPW = 32 / SG::LANES;
+        const int wl = threadIdx.x & 31;
+        ti = wl % TR; tj = wl / (TR * MPW);
+        grp = (threadIdx.x >> 5) * MPW + (wl / TR) % MPW;
+    } else {
+        grp = threadIdx.x / SG::LANES;
+        ti = (threadIdx.x % SG::LANES) / TC; tj = threadIdx.x % TC;
+    }
+    const bool lead = (ti == 0 && tj == 0);
     T *sm = smem + grp * SG::WORDS;
 
     #pragma unroll 1
     for (i64 base = (i64)blockIdx.x * SG::MPB; base < batch; base += (i64)gridDim.x * SG::MPB) {
         const i64 m = base + grp;
         const bool valid = m < batch;
-        const T *__restrict__ src = io.src(valid ? m : batch - 1);
+        const T *__restrict__ src;
+        T *__restrict__ dst;
+        int nn = N;                                                // order of the matrix inside the N x N tile
+        i64 iidx = m;                                              // where its info goes
+        if constexpr (IoTraits<IO>::PADDED) {
+            const MixedItem it = io.items[valid ? m : batch - 1];
+            src = static_cast<const T *>(it.in); dst = static_cast<T *>(it.out); nn = it.n; iidx = it.index;
+        } else {
+            src = io.src(valid ? m : batch - 1); dst = io.dst(valid ? m : batch - 1);
+        }
 
         PR ap[H][SC];                                              // ap[i][c] = T(rows 2i, 2i+1 ; column c), T = -A
         {
             T a[SR][SC];
-            tile_load_upper<T, N, TR, TC, false>(a, src, ti, tj);
+            if constexpr (IoTraits<IO>::PADDED) tile_load_upper_padded<T, N, TR, TC>(a, src, nn, ti, tj);
+            else tile_load_upper<T, N, TR, TC, false>(a, src, ti, tj);
             #pragma unroll
             for (int i = 0; i < H; ++i)
                 #pragma unroll
@@ -271,21 +388,58 @@ sweep_spd_kernel(IO io, i64 batch, int *__restrict__ info) {
         }
 
         T dmin = T(1), d = T(1);                                   // smallest pivot so far / current pivot
-        sweep_publish<T, N, TR, TC, 0, 0, 0>(ap, sm, ti, tj, 0);
+        T acc_m = T(0), acc_q = T(0);
+        PR rhs[SG::NC];                                            // unused in this mode
+        sweep_publish<T, N, TR, TC, SWEEP_INVERSE, 0, 0, 0>(ap, rhs, sm, ti, tj, 0);
         tile_sync<SG::LANES>();
-        SweepRanges<T, N, TR, TC, UNROLL, 0>::run(ap, sm, ti, tj, dmin, d);
+        SweepRanges<T, N, TR, TC, SWEEP_INVERSE, UNROLL, 0, 0, 0>::run(ap, rhs, sm, ti, tj, dmin, d, acc_m, acc_q);
 
-        if (!valid) continue;
-        T *__restrict__ dst = io.dst(m);
         // a NaN pivot turns every later pivot into NaN, so the last one tells; otherwise the minimum does
-        const bool bad = !(dmin > T(0)) || !(d == d);
+        const bool bad = valid && (!(dmin > T(0)) || !(d == d));
         int st = 0;
-        if (bad) {                                                 // rare: LAPACK's natural-order index, dst as scratch
-            if (lane == 0) { st = exact_potrf_info<T>(src, dst, N); if (st == 0) st = N; }
-            if (SG::LANES <= 32) st = __shfl_sync(__activemask(), st, (threadIdx.x & 31 & ~(SG::LANES - 1)));
-            else { __syncthreads(); if (lane == 0) sm[0] = (T)st; __syncthreads(); st = (int)sm[0]; __syncthreads(); }
+        if (SG::LANES <= 32) {                                     // rare: LAPACK's natural-order index, dst as scratch
+            if (__any_sync(0xffffffffu, bad)) {
+                if (bad && lead) { st = exact_potrf_info<T>(src, dst, nn); if (st == 0) st = nn; }
+                __syncwarp();                                      // scratch use ends before the NaN fill
+            }
+        } else if (bad) {                                          // one matrix per CTA: uniform
+            if (lead) { st = exact_potrf_info<T>(src, dst, nn); if (st == 0) st = nn; }
+            __syncthreads();
         }
-        if (lane == 0 && info) info[m] = st;
+        if (!valid) continue;
+        if (lead && info) info[iidx] = st;
+        if constexpr (IoTraits<IO>::PADDED) {                      // bounds-checked scalar stores, lda = nn
+            #pragma unroll
+            for (int g = 0; g < SG::NGR; ++g) {
+                #pragma unroll
+                for (int h = 0; h < SG::NGC; ++h) {
+                    const int br = TR * g + ti, bc = TC * h + tj;
+                    if (bad) {
+                        #pragma unroll
+                        for (int w = 0; w < 4; ++w)
+                            #pragma unroll
+                            for (int v = 0; v < 4; ++v)
+                                if (4 * br + w < nn && 4 * bc + v < nn) dst[(size_t)(4 * bc + v) * nn + 4 * br + w] = dev_nan<T>();
+                        continue;
+                    }
+                    if (SG::upper(2 * g, 4 * h) || br < bc) continue;
+                    #pragma unroll
+                    for (int w = 0; w < 4; ++w)
+                        #pragma unroll
+                        for (int v = 0; v < 4; ++v) {
+                            const int r = 4 * br + w, c = 4 * bc + v;
+                            if (r >= nn || c >= nn) continue;
+                            // static register indices only: element (w, v) and, on a diagonal block, its mirror (v, w)
+                            const T e_wv = ((4 * g + w) % 2) ? ap[(4 * g + w) / 2][4 * h + v].hi() : ap[(4 * g + w) / 2][4 * h + v].lo();
+                            const T e_vw = ((4 * g + v) % 2) ? ap[(4 * g + v) / 2][4 * h + w].hi() : ap[(4 * g + v) / 2][4 * h + w].lo();
+                            const T e = (br == bc && v > w) ? e_vw : e_wv;
+                            dst[(size_t)c * nn + r] = e;
+                            if (br > bc) dst[(size_t)r * nn + c] = e;
+                        }
+                }
+            }
+            continue;
+        }
         #pragma unroll
         for (int g = 0; g < SG::NGR; ++g) {
             #pragma unroll
@@ -319,6 +473,96 @@ sweep_spd_kernel(IO io, i64 batch, int *__restrict__ info) {
                 }
             }
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Fused GP mean / variance (reference src/gauss_bench.cu:127-265, 275-409 in ONE launch) on the same
+// machinery: B is loaded with diag(C) added, only the factor part of the sweep is executed (dead rows
+// and columns pruned statically), the two right-hand sides ride along distributed over the thread
+// columns, and with A = L D L^T the scalars are  sum_k u_k v_k / d_k  and  E - sum_k u_k^2 / d_k.
+// Nothing but the scalars is written.  scratch: N*N words per matrix slot, used only to recompute
+// LAPACK's natural-order info for a flagged (non-SPD) matrix.
+// ------------------------------------------------------------------------------------------
+template <typename T, int N, int TR, int TC, bool UNROLL, int MINB>
+__global__ void __launch_bounds__((SweepGeo<N, TR, TC>::BLOCK), MINB)
+sweep_gp_kernel(GpIO<T> io, i64 batch, int *__restrict__ info, T *__restrict__ scratch) {
+    using SG = SweepGeo<N, TR, TC>;
+    using PR = Pair2<T>;
+    constexpr int SR = SG::SR, SC = SG::SC, H = SG::H;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *smem = reinterpret_cast<T *>(smem_raw);
+
+    const int grp = threadIdx.x / SG::LANES;
+    const int ti = (threadIdx.x % SG::LANES) / TC, tj = threadIdx.x % TC;
+    const bool lead = (ti == 0 && tj == 0);
+    T *sm = smem + grp * SG::WORDS;
+
+    #pragma unroll 1
+    for (i64 base = (i64)blockIdx.x * SG::MPB; base < batch; base += (i64)gridDim.x * SG::MPB) {
+        const i64 m = base + grp;
+        const bool valid = m < batch;
+        const i64 mm = valid ? m : batch - 1;
+        const T *__restrict__ src = io.b + mm * (i64)(N * N);
+        const T *__restrict__ cv = io.c + mm * N;
+
+        PR ap[H][SC];
+        {
+            T a[SR][SC];
+            tile_load_upper<T, N, TR, TC, false>(a, src, ti, tj);
+            // + diag(C) on load: only threads holding a diagonal sub-block see diagonal elements
+            #pragma unroll
+            for (int g = 0; g < SG::NGR; ++g)
+                #pragma unroll
+                for (int h = 0; h < SG::NGC; ++h) {
+                    if (TR * g > TC * h + TC - 1 || TR * g + TR - 1 < TC * h) continue;
+                    if (TR * g + ti == TC * h + tj) {
+                        T c0, c1, c2, c3;
+                        ldg4(cv + 4 * (TR * g + ti), c0, c1, c2, c3);
+                        a[4 * g][4 * h] += c0; a[4 * g + 1][4 * h + 1] += c1;
+                        a[4 * g + 2][4 * h + 2] += c2; a[4 * g + 3][4 * h + 3] += c3;
+                    }
+                }
+            #pragma unroll
+            for (int i = 0; i < H; ++i)
+                #pragma unroll
+                for (int c = 0; c < SC; ++c) ap[i][c] = PR::make(-a[2 * i][c], -a[2 * i + 1][c]);
+        }
+        PR rhs[SG::NC];
+        {
+            const T *__restrict__ av = io.a + mm * N;
+            const T *__restrict__ dv = (io.d ? io.d : io.a) + mm * N;
+            #pragma unroll
+            for (int j = 0; j < SG::NC; ++j) {
+                const int cb = tj + TC * j, ip = cb % H;
+                const T *p = (cb / H == 0 ? av : dv) + 4 * (TR * (ip / 2) + ti) + 2 * (ip % 2);
+                rhs[j] = PR::make(p[0], p[1]);                     // lanes beyond 2 H combinations hold copies nobody reads
+            }
+        }
+
+        T dmin = T(1), d = T(1), acc_m = T(0), acc_q = T(0);
+        sweep_publish<T, N, TR, TC, SWEEP_GP, 0, 0, 0>(ap, rhs, sm, ti, tj, 0);
+        tile_sync<SG::LANES>();
+        SweepRanges<T, N, TR, TC, SWEEP_GP, UNROLL, 0, 0, 0>::run(ap, rhs, sm, ti, tj, dmin, d, acc_m, acc_q);
+
+        const bool bad = valid && (!(dmin > T(0)) || !(d == d));
+        if (!valid || !lead) continue;
+        if (bad) {                                    // rare: report LAPACK's natural-order index
+            T *w = scratch + ((i64)blockIdx.x * SG::MPB + grp) * (i64)(N * N);
+            for (int j = 0; j < N; ++j) {
+                for (int i = 0; i < j; ++i) w[(size_t)j * N + i] = src[(size_t)j * N + i];
+                w[(size_t)j * N + j] = src[(size_t)j * N + j] + cv[j];
+            }
+            int st = exact_potrf_info_inplace<T>(w, N);
+            if (st == 0) st = N;
+            if (io.means) io.means[m] = dev_nan<T>();
+            if (io.variances) io.variances[m] = dev_nan<T>();
+            if (info) info[m] = st;
+            continue;
+        }
+        if (io.means) io.means[m] = acc_m;
+        if (io.variances) io.variances[m] = io.e[m] - acc_q;
+        if (info) info[m] = 0;
     }
 }
 

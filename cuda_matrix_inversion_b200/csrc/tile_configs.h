@@ -76,3 +76,17 @@
 #define INVGPU_SWEEP_F64(X)                                                                     \
     X(0, double, 16, 2, 2, false, 2) X(0, double, 32, 4, 4, false, 2) X(0, double, 64, 8, 8, false, 4) X(0, double, 128, 16, 16, false, 1)
 #define INVGPU_SWEEP_ALL(X) INVGPU_SWEEP_F32(X) INVGPU_SWEEP_F64(X)
+
+// fused GP mean / variance on the sweep machinery (sweep_gp_kernel):  X(T, N, TR, TC, UNROLL, MINB)
+// Measured on B200 against the three-phase tile kernels above (fraction of the HBM roofline, sweep vs tile):
+// fp32 n = 32: 0.45 vs 0.57, 64: 0.23 vs 0.39, 128: 0.118 vs 0.092; fp64 32/64/128: equal within 5 %.
+// Only the CTA tier gains (one barrier per pivot instead of the rolled potrf's per-pivot chain), so only
+// that one is dispatched; the warp tiers stay on the fully unrolled tile kernels with exact static pruning.
+#define INVGPU_SWEEP_GP_F32(X) X(float, 128, 8, 16, false, 3)
+#define INVGPU_SWEEP_GP_F64(X)
+#define INVGPU_SWEEP_GP_ALL(X) INVGPU_SWEEP_GP_F32(X) INVGPU_SWEEP_GP_F64(X)
+
+// mixed-dimension batches on the sweep kernel with the padded IO policy:  X(T, N, TR, TC, MINB); tiers in ascending N
+#define INVGPU_SWEEP_PAD_F32(X) X(float, 16, 2, 2, 4) X(float, 32, 2, 4, 3) X(float, 64, 4, 8, 3) X(float, 128, 8, 16, 3) X(float, 256, 16, 16, 1)
+#define INVGPU_SWEEP_PAD_F64(X) X(double, 16, 2, 2, 2) X(double, 32, 4, 4, 2) X(double, 64, 8, 8, 4) X(double, 128, 16, 16, 1)
+#define INVGPU_SWEEP_PAD_ALL(X) INVGPU_SWEEP_PAD_F32(X) INVGPU_SWEEP_PAD_F64(X)

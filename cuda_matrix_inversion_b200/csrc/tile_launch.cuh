@@ -22,6 +22,12 @@ int launch_onesweep(StridedIO<T> io, i64 batch, int *dInfo, cudaStream_t st, Dev
 template <typename T, int N, int TR, int TC, bool UNROLL, int MINB>
 int launch_sweep(StridedIO<T> io, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds);
 
+template <typename T, int N, int TR, int TC, bool UNROLL, int MINB>
+int launch_sweep_gp(GpIO<T> io, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds);
+
+template <typename T, int N, int TR, int TC, int MINB>
+int launch_sweep_pad(PadIO<T> io, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds);
+
 }  // namespace invgpu
 
 #ifdef INVGPU_TILE_DEFINE
@@ -41,6 +47,49 @@ int launch_sweep(StridedIO<T> io, i64 batch, int *dInfo, cudaStream_t st, Device
     int rc = persistent_grid(kern, SG::BLOCK, smem, (batch + SG::MPB - 1) / SG::MPB, ds, &grid);
     if (rc) return rc;
     kern<<<grid, SG::BLOCK, smem, st>>>(io, batch, dInfo);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return (int)cudaGetLastError();
+}
+
+template <typename T, int N, int TR, int TC, int MINB>
+int launch_sweep_pad(PadIO<T> io, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds) {
+    using SG = SweepGeo<N, TR, TC>;
+    auto kern = sweep_spd_kernel<T, N, TR, TC, false, PadIO<T>, MINB>;
+    const size_t smem = (size_t)SG::MPB * SG::WORDS * sizeof(T);
+    int grid = 0;
+    int rc = persistent_grid(kern, SG::BLOCK, smem, (batch + SG::MPB - 1) / SG::MPB, ds, &grid);
+    if (rc) return rc;
+    kern<<<grid, SG::BLOCK, smem, st>>>(io, batch, dInfo);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return (int)cudaGetLastError();
+}
+
+// scratch for the (rare) natural-order info recomputation of flagged GP matrices
+static int ensure_gp_scratch(DeviceState *ds, size_t need) {
+    if (ds->gp_scratch_bytes < need) {
+        static std::mutex scratch_mutex;              // not engine_mutex(): the host pipeline holds that one
+        std::lock_guard<std::mutex> lk(scratch_mutex);
+        if (ds->gp_scratch_bytes < need) {
+            if (ds->gp_scratch) cudaFree(ds->gp_scratch);
+            ds->gp_scratch = nullptr; ds->gp_scratch_bytes = 0;
+            INVGPU_TRY(cudaMalloc(&ds->gp_scratch, need));
+            ds->gp_scratch_bytes = need;
+        }
+    }
+    return 0;
+}
+
+template <typename T, int N, int TR, int TC, bool UNROLL, int MINB>
+int launch_sweep_gp(GpIO<T> io, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds) {
+    using SG = SweepGeo<N, TR, TC>;
+    auto kern = sweep_gp_kernel<T, N, TR, TC, UNROLL, MINB>;
+    const size_t smem = (size_t)SG::MPB * SG::WORDS * sizeof(T);
+    int grid = 0;
+    int rc = persistent_grid(kern, SG::BLOCK, smem, (batch + SG::MPB - 1) / SG::MPB, ds, &grid);
+    if (rc) return rc;
+    rc = ensure_gp_scratch(ds, (size_t)grid * SG::MPB * N * N * sizeof(T));
+    if (rc) return rc;
+    kern<<<grid, SG::BLOCK, smem, st>>>(io, batch, dInfo, (T *)ds->gp_scratch);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return (int)cudaGetLastError();
 }
@@ -94,18 +143,8 @@ int launch_tile_gp(GpIO<T> io, i64 batch, int *dInfo, cudaStream_t st, DeviceSta
     int grid = 0;
     int rc = persistent_grid(kern, G::BLOCK, smem, (batch + G::MPB - 1) / G::MPB, ds, &grid);
     if (rc) return rc;
-    // scratch for the (rare) natural-order info recomputation of flagged matrices
-    const size_t need = (size_t)grid * G::MPB * N * N * sizeof(T);
-    if (ds->gp_scratch_bytes < need) {
-        static std::mutex scratch_mutex;              // not engine_mutex(): the host pipeline holds that one
-        std::lock_guard<std::mutex> lk(scratch_mutex);
-        if (ds->gp_scratch_bytes < need) {
-            if (ds->gp_scratch) cudaFree(ds->gp_scratch);
-            ds->gp_scratch = nullptr; ds->gp_scratch_bytes = 0;
-            INVGPU_TRY(cudaMalloc(&ds->gp_scratch, need));
-            ds->gp_scratch_bytes = need;
-        }
-    }
+    rc = ensure_gp_scratch(ds, (size_t)grid * G::MPB * N * N * sizeof(T));
+    if (rc) return rc;
     kern<<<grid, G::BLOCK, smem, st>>>(io, batch, dInfo, (T *)ds->gp_scratch);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return (int)cudaGetLastError();
@@ -120,6 +159,10 @@ int launch_tile_gp(GpIO<T> io, i64 batch, int *dInfo, cudaStream_t st, DeviceSta
     template int invgpu::launch_gj<T, N, ROWS, invgpu::PtrIO<T>, MINB>(invgpu::PtrIO<T>, int, invgpu::i64, int *, cudaStream_t, invgpu::DeviceState *);
 #define INVGPU_ONESWEEP_INSTANTIATE(T, N, TR, TC, STAGE, MINB) \
     template int invgpu::launch_onesweep<T, N, TR, TC, STAGE, MINB>(invgpu::StridedIO<T>, invgpu::i64, int *, cudaStream_t, invgpu::DeviceState *);
+#define INVGPU_SWEEP_PAD_INSTANTIATE(T, N, TR, TC, MINB) \
+    template int invgpu::launch_sweep_pad<T, N, TR, TC, MINB>(invgpu::PadIO<T>, invgpu::i64, int *, cudaStream_t, invgpu::DeviceState *);
+#define INVGPU_SWEEP_GP_INSTANTIATE(T, N, TR, TC, UNROLL, MINB) \
+    template int invgpu::launch_sweep_gp<T, N, TR, TC, UNROLL, MINB>(invgpu::GpIO<T>, invgpu::i64, int *, cudaStream_t, invgpu::DeviceState *);
 #define INVGPU_SWEEP_INSTANTIATE(V, T, N, TR, TC, UNROLL, MINB) \
     template int invgpu::launch_sweep<T, N, TR, TC, UNROLL, MINB>(invgpu::StridedIO<T>, invgpu::i64, int *, cudaStream_t, invgpu::DeviceState *);
 #define INVGPU_TILE_INSTANTIATE_GP(T, N, TR, TC, MINB) \

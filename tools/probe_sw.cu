@@ -1,4 +1,4 @@
-// compile-only probe for the sweep kernel
+// compile-only probe for the sweep kernels
 #include "../cuda_matrix_inversion_b200/csrc/generic_smem.cuh"
 #include "../cuda_matrix_inversion_b200/csrc/sweep_kernels.cuh"
 using namespace invgpu;
@@ -9,10 +9,10 @@ using namespace invgpu;
 #define PN 32
 #endif
 #ifndef PTR
-#define PTR 4
+#define PTR 2
 #endif
 #ifndef PTC
-#define PTC 2
+#define PTC 4
 #endif
 #ifndef PUNROLL
 #define PUNROLL false
@@ -20,4 +20,8 @@ using namespace invgpu;
 #ifndef PMINB
 #define PMINB 3
 #endif
+#ifdef PGP
+template __global__ void invgpu::sweep_gp_kernel<PT, PN, PTR, PTC, PUNROLL, PMINB>(GpIO<PT>, i64, int *, PT *);
+#else
 template __global__ void invgpu::sweep_spd_kernel<PT, PN, PTR, PTC, PUNROLL, StridedIO<PT>, PMINB>(StridedIO<PT>, i64, int *);
+#endif

@@ -43,6 +43,10 @@ BATCH = 1 << 20
 METRIC = "batched SPD inversions/sec (32x32 fp32)"
 UNIT = "inversions/s"
 WORKLOAD = "synthetic batched SPD Cholesky inverse, 2^20 x 32x32 fp32 per GPU (BASELINE configs[2])"
+# dram__bytes_read.sum + dram__bytes_write.sum of the headline kernel from the committed `ncu --set full` capture
+# (2^18 matrices per launch there: 1.073962 GB read + 1.029978 GB written), scaled to the 2^20 of one bench launch
+NCU_DRAM_BYTES_PER_LAUNCH = int((1.073962e9 + 1.029978e9) * 4)
+NCU_TRAFFIC_SOURCE = "profiles/r1_sweep32_summary.md (ncu --set full, 2^18 matrices) x 4"
 
 
 def _peaks():
@@ -198,6 +202,7 @@ def _extras(torch, api, steps, warmup, hbm_peak):
     inv_case("spd_16_f32", 16, 1 << 21, f32)
     inv_case("spd_32_f64", 32, 1 << 19, f64)
     inv_case("spd_64_f32", 64, 1 << 17, f32)
+    inv_case("spd_64_f64", 64, 1 << 16, f64)
     inv_case("spd_128_f32", 128, 1 << 15, f32)
     inv_case("gauss_jordan_64_f32", 64, 1 << 15, f32, general=True)
 
@@ -213,6 +218,7 @@ def _extras(torch, api, steps, warmup, hbm_peak):
         out[key] = {"evals_per_s": batch / (ms * 1e-3), "ms": ms, "algorithmic_GBps": gbs,
                     "hbm_frac": gbs / hbm_peak, "tier": api.tier_name("gp", n)}
 
+    gp_case("gp_mean_32_f32", 32, 1 << 19)
     gp_case("gp_mean_64_f32", 64, 100 * 1600)
     gp_case("gp_mean_128_f32_25k", 128, 25000)
 
@@ -243,8 +249,8 @@ def _extras(torch, api, steps, warmup, hbm_peak):
     ms = float(np.median(t))
     gbs = 2 * 4 * total / (ms * 1e-3) / 1e9
     out["mixed_500k_f32"] = {"matrices_per_s": cnt / (ms * 1e-3), "ms": ms, "algorithmic_GBps": gbs, "hbm_frac": gbs / hbm_peak,
-                             "flagged": int((info != 0).sum()), "tier": "persistent-CTA scheduler over 32/128/256 buckets (generic smem math)",
-                             "note": "timing includes the host-side bucketing/sort and work-list upload"}
+                             "flagged": int((info != 0).sum()), "tier": "persistent grids over five padded sweep tiers (16/32/64/128/256), counting-sort work lists",
+                             "note": "timing includes the host-side planning (~6.5 ms) and work-list upload"}
     return out
 
 
@@ -345,11 +351,12 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "n": N, "batch_per_gpu": BATCH, "algorithm": "potrf+trtri+lauum",
+            "config": {"workload": WORKLOAD, "n": N, "batch_per_gpu": BATCH, "algorithm": "Cholesky-route inverse (potrf+trtri+lauum merged into one symmetric sweep, sweep_kernels.cuh)",
                        "l2_policy": "inputs+outputs 8.6 GB per step >> 126 MB L2", "sharding": f"dp{world}",
                        "kernel_tier": api.tier_name("spd", N)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / hbm_peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH, "traffic_source": NCU_TRAFFIC_SOURCE,
+                         "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": kernel_ms},
             "cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": cores, "kind": kind,
                              "sample": f"{1 << 18} matrices (1/4 of the GPU batch), best of 3, {what}, "

@@ -133,7 +133,13 @@ static int fast_padded(PadIO<T> io, int tier_n, i64 batch, int *dInfo, cudaStrea
     if (op == 2 && n == N && dtype_bytes == (int)sizeof(TT)) return TR * TC <= 32 ? "warp-tile" : "cta-tile";
 #define INVGPU_GJ_NAME(TT, N, ROWS, MINB) \
     if (op == 1 && n <= N && dtype_bytes == (int)sizeof(TT)) return "warp-rowlane";
+#define INVGPU_SWEEP_NAME(V, TT, N, TR, TC, UNROLL, MINB) \
+    if (op == 0 && V == 0 && n == N && n >= INVGPU_SWEEP_MIN_N && dtype_bytes == (int)sizeof(TT)) return TR * TC <= 32 ? "sweep-warp" : "sweep-cta";
+#define INVGPU_SWEEP_GP_NAME(TT, N, TR, TC, UNROLL, MINB) \
+    if (op == 2 && n == N && dtype_bytes == (int)sizeof(TT)) return TR * TC <= 32 ? "sweep-warp" : "sweep-cta";
 static const char *fast_tier_name(int op, int n, int dtype_bytes) {
+    INVGPU_SWEEP_ALL(INVGPU_SWEEP_NAME)
+    INVGPU_SWEEP_GP_ALL(INVGPU_SWEEP_GP_NAME)
     INVGPU_GJ_ALL(INVGPU_GJ_NAME)
     INVGPU_TILE_SPD_ALL(INVGPU_TILE_NAME)
     INVGPU_TILE_GP_ALL(INVGPU_TILE_NAME_GP)

@@ -124,6 +124,32 @@ def test_spd_flags_match_oracle(api, fixtures_dir, dtype):
     assert info[0] == 2
 
 
+@pytest.mark.parametrize("n", [16, 32, 64, 128])
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_spd_flags_sweep_tiers(api, n, dtype):
+    """The sweep tiers eliminate in a permuted order; a flagged matrix must still report LAPACK's
+    natural-order spotrf info (reference src/inverse.c:92-95) and come back as NaN."""
+    a = spd_batch(n, 10, np.float64, seed=21 + n)
+    k0 = n // 2 + 3
+    d = np.ones(n)
+    d[k0 - 1] = -1.0
+    a[1] = np.diag(d)                                             # indefinite: info k0
+    a[3, n - 1, n - 1] = np.nan                                   # NaN in the last pivot: info n
+    a[4] = 1.1                                                    # rank one: info 2
+    a[6] = -np.eye(n)                                             # negative definite: info 1
+    w = np.linalg.eigvalsh(a[8])
+    a[8] -= (w[0] + 0.5 * (w[1] - w[0])) * np.eye(n)              # one clearly negative eigenvalue: the oracle says where
+    flat = orc.to_colmajor(a.astype(dtype))
+    got, info = api.spd_inverse_host(flat, n, out=np.full_like(flat, 777.0))
+    want, oinfo = orc.chol_inverse(flat, n)
+    np.testing.assert_array_equal(info, oinfo)
+    assert info[1] == k0 and info[3] == n and info[4] == 2 and info[6] == 1 and info[8] > 0
+    good = info == 0
+    assert good.sum() == 5
+    assert normwise_err(orc.from_colmajor(got, n)[good], orc.from_colmajor(want, n)[good]) <= TOL[np.dtype(dtype)]
+    assert np.isnan(orc.from_colmajor(got, n)[~good]).all()
+
+
 @pytest.mark.parametrize("n", [4, 16, 33, 64])
 @pytest.mark.parametrize("dtype", DTYPES)
 def test_spd_factor(api, torch, n, dtype):
@@ -292,6 +318,25 @@ def test_gp_flags(api):
     _, oinfo = orc.gp_mean(n, flat["a"], flat["b"], flat["c"], flat["d"])
     np.testing.assert_array_equal(info, oinfo)
     assert info[3] == 1 and info.sum() == 1
+
+
+@pytest.mark.parametrize("n", [64, 128])
+def test_gp_flags_cta_tiers(api, n):
+    """fp32 n = 128 runs on the sweep GP kernel (permuted order): flags must still be LAPACK's."""
+    g = gp_batch(n, 5, np.float32, seed=19)
+    g["b"][1] = -g["b"][1]
+    d = np.ones(n, dtype=np.float32)
+    d[n // 3] = -5.0
+    g["b"][3] = np.diag(d)                                        # with C >= 0 added the pivot n//3 stays negative
+    g["c"][3] = 0.5
+    flat = {k: orc.to_colmajor(v) if v.ndim == 3 else v.reshape(-1) for k, v in g.items()}
+    means, var, info = api.gp_host(n, flat["a"], flat["b"], flat["c"], flat["d"], flat["e"])
+    om, oinfo = orc.gp_mean(n, flat["a"], flat["b"], flat["c"], flat["d"])
+    np.testing.assert_array_equal(info, oinfo)
+    assert info[1] == 1 and info[3] == n // 3 + 1 and (info != 0).sum() == 2
+    good = info == 0
+    assert np.abs(means[good] - om[good]).max() <= 1e-4
+    assert np.isnan(means[~good]).all()
 
 
 # --------------------------------------------------------------------------------------- legacy symbols

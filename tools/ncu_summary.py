@@ -39,11 +39,11 @@ def main():
     if len(sys.argv) > 3:
         rows = [r for r in csv.reader(open(sys.argv[3])) if len(r) > 5]
         h = rows[0]
-        ki, vi = h.index("Kernel Name"), h.index("Metric Value")
+        ki, vi, gi = h.index("Kernel Name"), h.index("Metric Value"), h.index("Grid Size")
         agg = collections.defaultdict(list)
         for r in rows[1:]:
             try:
-                agg[r[ki][:110]].append(float(r[vi].replace(",", "")))
+                agg[r[ki][:110] + " grid " + r[gi]].append(float(r[vi].replace(",", "")))
             except ValueError:
                 pass
         lines += ["", f"## launch list of `{sys.argv[3]}` (gpu__time_duration, cold-cache / serialised)", "",

@@ -71,8 +71,8 @@
 #define INVGPU_SWEEP_F32(X)                                                                     \
     X(0, float, 16, 2, 2, false, 4) X(1, float, 16, 1, 2, false, 3)                             \
     X(0, float, 32, 2, 4, false, 3) X(1, float, 32, 4, 2, false, 3) X(2, float, 32, 4, 4, false, 5) X(3, float, 32, 2, 4, true, 3) \
-    X(0, float, 64, 4, 8, false, 3) X(1, float, 64, 8, 8, false, 8)                             \
-    X(0, float, 128, 8, 16, false, 3) X(1, float, 128, 16, 16, false, 2)
+    X(0, float, 64, 4, 8, false, 3) X(1, float, 64, 8, 8, false, 8) X(2, float, 64, 4, 8, true, 3) X(3, float, 64, 8, 4, false, 3) \
+    X(0, float, 128, 8, 16, false, 3) X(1, float, 128, 16, 16, false, 2) X(2, float, 128, 8, 16, true, 3) X(3, float, 128, 16, 8, false, 3)
 #define INVGPU_SWEEP_F64(X)                                                                     \
     X(0, double, 16, 2, 2, false, 2) X(0, double, 32, 4, 4, false, 2) X(0, double, 64, 8, 8, false, 4) X(0, double, 128, 16, 16, false, 1)
 #define INVGPU_SWEEP_ALL(X) INVGPU_SWEEP_F32(X) INVGPU_SWEEP_F64(X)

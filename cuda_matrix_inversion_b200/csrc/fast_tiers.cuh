@@ -34,9 +34,16 @@ static bool dense_aligned(const StridedIO<T> &io, int n) {
     if (std::is_same<T, TT>::value && n == N)                                                        \
         return launch_onesweep<TT, N, TR, TC, STAGE, MINB>(*reinterpret_cast<StridedIO<TT> *>(&io), batch, dInfo, st, ds);
 
-#define INVGPU_SWEEP_TRY(V, TT, N, TR, TC, UNROLL, MINB)                                            \
+#define INVGPU_SWEEP_TRY(V, TT, N, TR, TC, UNROLL, MINB, BLK)                                       \
     if (std::is_same<T, TT>::value && n == N && V == variant)                                        \
-        return launch_sweep<TT, N, TR, TC, UNROLL, MINB>(*reinterpret_cast<StridedIO<TT> *>(&io), batch, dInfo, st, ds);
+        return launch_sweep<TT, N, TR, TC, UNROLL, MINB, BLK>(*reinterpret_cast<StridedIO<TT> *>(&io), batch, dInfo, st, ds);
+
+#define INVGPU_SWEEP_TMA_TRY(V, TT, N, TR, TC, UNROLL, MINB)                                         \
+    if (std::is_same<T, TT>::value && n == N && V == variant) {                                      \
+        const int rc_tma = launch_sweep_tma<TT, N, TR, TC, UNROLL, MINB>(*reinterpret_cast<StridedIO<TT> *>(&io), batch, dInfo, st, ds); \
+        if (rc_tma != INVGPU_TMA_UNAVAILABLE) return rc_tma;                                          \
+        variant = 0;                                                                                 \
+    }
 
 // INVGPU_SPD_KERNEL=threesweep selects the three-sweep tile kernels for the sizes both families cover
 static bool prefer_onesweep() {
@@ -56,7 +63,10 @@ static int fast_spd_dense(StridedIO<T> io, int n, i64 batch, int *dInfo, cudaStr
         if (env_variant < 0) { const char *e = getenv("INVGPU_SWEEP_VARIANT"); env_variant = e ? atoi(e) : 0; }
         int variant = env_variant;
         if (old < 0) { const char *e = getenv("INVGPU_SPD_KERNEL"); old = (e && !strcmp(e, "onesweep")) ? 1 : 0; }
-        if (!old && n >= INVGPU_SWEEP_MIN_N) { INVGPU_SWEEP_ALL(INVGPU_SWEEP_TRY) }
+        if (!old && n >= INVGPU_SWEEP_MIN_N) {
+            INVGPU_SWEEP_TMA_ALL(INVGPU_SWEEP_TMA_TRY)             // falls through when the batch is not TMA-describable
+            INVGPU_SWEEP_ALL(INVGPU_SWEEP_TRY)
+        }
         INVGPU_ONESWEEP_ALL(INVGPU_ONESWEEP_TRY)
         if (!old) { variant = 0; INVGPU_SWEEP_ALL(INVGPU_SWEEP_TRY) }
     }
@@ -100,9 +110,9 @@ static int fast_general(IO io, int n, i64 batch, int *dInfo, cudaStream_t st, De
     if (std::is_same<T, TT>::value && n == N)                                                        \
         return launch_tile_gp<TT, N, TR, TC, MINB>(*reinterpret_cast<GpIO<TT> *>(&io), batch, dInfo, st, ds);
 
-#define INVGPU_SWEEP_TRY_GP(TT, N, TR, TC, UNROLL, MINB)                                            \
-    if (std::is_same<T, TT>::value && n == N)                                                        \
-        return launch_sweep_gp<TT, N, TR, TC, UNROLL, MINB>(*reinterpret_cast<GpIO<TT> *>(&io), batch, dInfo, st, ds);
+#define INVGPU_SWEEP_TRY_GP(V, TT, N, TR, TC, UNROLL, MINB, BLK)                                    \
+    if (std::is_same<T, TT>::value && n == N && V == variant)                                        \
+        return launch_sweep_gp<TT, N, TR, TC, UNROLL, MINB, BLK>(*reinterpret_cast<GpIO<TT> *>(&io), batch, dInfo, st, ds);
 
 template <typename T>
 static int fast_gp(GpIO<T> io, int n, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds) {
@@ -110,6 +120,8 @@ static int fast_gp(GpIO<T> io, int n, i64 batch, int *dInfo, cudaStream_t st, De
     if (all % 16 != 0 || ((size_t)n * sizeof(T)) % 16 != 0) return INVGPU_NO_FAST_PATH;
     static int old = -1;                              // INVGPU_GP_KERNEL=tile keeps the three-phase tile kernels
     if (old < 0) { const char *e = getenv("INVGPU_GP_KERNEL"); old = (e && !strcmp(e, "tile")) ? 1 : 0; }
+    static int variant = -1;                          // INVGPU_SWEEP_VARIANT=V: another instantiated configuration
+    if (variant < 0) { const char *e = getenv("INVGPU_SWEEP_VARIANT"); variant = e ? atoi(e) : 0; }
     if (!old) { INVGPU_SWEEP_GP_ALL(INVGPU_SWEEP_TRY_GP) }
     INVGPU_TILE_GP_ALL(INVGPU_TILE_TRY_GP)
     return INVGPU_NO_FAST_PATH;
@@ -133,10 +145,10 @@ static int fast_padded(PadIO<T> io, int tier_n, i64 batch, int *dInfo, cudaStrea
     if (op == 2 && n == N && dtype_bytes == (int)sizeof(TT)) return TR * TC <= 32 ? "warp-tile" : "cta-tile";
 #define INVGPU_GJ_NAME(TT, N, ROWS, MINB) \
     if (op == 1 && n <= N && dtype_bytes == (int)sizeof(TT)) return "warp-rowlane";
-#define INVGPU_SWEEP_NAME(V, TT, N, TR, TC, UNROLL, MINB) \
+#define INVGPU_SWEEP_NAME(V, TT, N, TR, TC, UNROLL, MINB, BLK) \
     if (op == 0 && V == 0 && n == N && n >= INVGPU_SWEEP_MIN_N && dtype_bytes == (int)sizeof(TT)) return TR * TC <= 32 ? "sweep-warp" : "sweep-cta";
-#define INVGPU_SWEEP_GP_NAME(TT, N, TR, TC, UNROLL, MINB) \
-    if (op == 2 && n == N && dtype_bytes == (int)sizeof(TT)) return TR * TC <= 32 ? "sweep-warp" : "sweep-cta";
+#define INVGPU_SWEEP_GP_NAME(V, TT, N, TR, TC, UNROLL, MINB, BLK) \
+    if (op == 2 && V == 0 && n == N && dtype_bytes == (int)sizeof(TT)) return TR * TC <= 32 ? "sweep-warp" : "sweep-cta";
 static const char *fast_tier_name(int op, int n, int dtype_bytes) {
     INVGPU_SWEEP_ALL(INVGPU_SWEEP_NAME)
     INVGPU_SWEEP_GP_ALL(INVGPU_SWEEP_GP_NAME)

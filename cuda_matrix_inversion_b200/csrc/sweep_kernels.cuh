@@ -135,6 +135,20 @@ struct SweepGeo {
     }
     // right-hand sides of the GP mode: combination cb = e H + ip (vector e, row pair ip) lives in lane cb % TC
     static constexpr int NC = (2 * H + TC - 1) / TC;
+    // ---- 2x2 block pivots (sweep2_*): two z lines, three pivot words (+1 pad), four right-hand-side words
+    static constexpr int LINE2 = 2 * N + 8;
+    static constexpr int WORDS2 = ((2 * LINE2 + 31) / 32) * 32 + (LANES < 32 ? 8 : 0);
+    // level (S, WP): row pairs / columns whose pivots are done for every thread (factor-only pruning)
+    __host__ __device__ static constexpr bool pair_dead2(int i, int S, int WP) {
+        return ((2 * i) / 4) / RG < S || (((2 * i) / 4) / RG == S && ((2 * i) % 4) / 2 < WP);
+    }
+    __host__ __device__ static constexpr bool col_dead2(int c, int S, int WP) {
+        return (c / 4) / CG < S || ((c / 4) / CG == S && (c % 4) / 2 < WP);
+    }
+    template <int MODE>
+    __host__ __device__ static constexpr bool skip2(int i, int c, int S, int WP) {
+        return upper(i, c) || (MODE == SWEEP_GP && (pair_dead2(i, S, WP) || col_dead2(c, S, WP)));
+    }
 };
 
 // element `odd` of a pair: read it and (inverse mode) zero it
@@ -311,6 +325,228 @@ struct SweepRanges {
     }
 };
 
+// ==========================================================================================
+// 2x2 BLOCK PIVOTS.  The pivots 4q+2wp, 4q+2wp+1 (one Pair2 row of the diagonal thread) are taken
+// together: with Z = [z1 z2] = T(:, K) raw, D = -T(K, K) and W = D^-1 the sweep of both is
+//     T_ic += (Z W)_i . Z_c ,   Z_K := -I   (the block form of the z_k = -1 convention),
+// i.e. one publish, one barrier, one reciprocal and one dependency chain per TWO pivots; the operands
+// X = Z W cost four packed multiplies per row pair instead of two.  The n = 64 / 128 tiers and the GP
+// kernel are bound by exactly that chain (profiles/r1_sweep64_summary.md), not by issue slots or pipes.
+// Line layout: z1[N] | z2[N] | p11 p21 p22 - | u1 v1 u2 v2   (p = raw T entries, u / v = right-hand sides).
+// Levels are (S, WP), WP = 0, 1: whole register pairs die together in the factor-only mode.
+// ==========================================================================================
+template <typename T, int N, int TR, int TC, int MODE, int GRN, int HCN, int WPN>
+__device__ __forceinline__ void sweep2_publish(Pair2<T> (&ap)[N / TR / 2][N / TC], Pair2<T> (&rhs)[SweepGeo<N, TR, TC>::NC],
+                                               T *zn, int ti, int tj, int qn) {
+    using SG = SweepGeo<N, TR, TC>;
+    using PR = Pair2<T>;
+    constexpr int sc1 = 4 * HCN + 2 * WPN, sc2 = sc1 + 1, ipn = (4 * GRN + 2 * WPN) / 2;
+    T *z1 = zn, *z2 = zn + N, *pw = zn + 2 * N;
+    const int rkn = qn % TR, ckn = qn % TC;
+    if (tj == ckn) {                                               // columns k1, k2: block rows below block qn
+        #pragma unroll
+        for (int g = GRN; g < SG::NGR; ++g) {
+            if (g > GRN || ti > rkn) {
+                const int o = 4 * (TR * g + ti);
+                sts_pair(z1 + o, ap[2 * g][sc1]); sts_pair(z1 + o + 2, ap[2 * g + 1][sc1]);
+                sts_pair(z2 + o, ap[2 * g][sc2]); sts_pair(z2 + o + 2, ap[2 * g + 1][sc2]);
+                if (MODE == SWEEP_INVERSE) { ap[2 * g][sc1].clear(); ap[2 * g + 1][sc1].clear(); ap[2 * g][sc2].clear(); ap[2 * g + 1][sc2].clear(); }
+            }
+        }
+    }
+    if (ti == rkn) {                                               // rows k1, k2 (one register pair): block columns left of qn
+        #pragma unroll
+        for (int h = 0; h <= HCN; ++h) {
+            if (h < HCN || tj < ckn) {
+                #pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    PR &p = ap[ipn][4 * h + v];
+                    sts_one(z1 + 4 * (TC * h + tj) + v, p.lo());
+                    sts_one(z2 + 4 * (TC * h + tj) + v, p.hi());
+                    if (MODE == SWEEP_INVERSE) p.clear();
+                }
+            }
+        }
+        if (tj == ckn) {                                           // diagonal thread: block qn of both lines, Z_K = -I
+            constexpr int a = 2 * WPN, b = a + 1;
+            T e1[4], e2[4];
+            #pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                if (v < a) {                                       // (rows a, b ; column v)
+                    PR &p = ap[ipn][4 * HCN + v];
+                    e1[v] = p.lo(); e2[v] = p.hi();
+                    if (MODE == SWEEP_INVERSE) p.clear();
+                } else if (v == a) {                               // T_aa, T_ba
+                    PR &p = ap[ipn][sc1];
+                    sts_one(pw + 0, p.lo()); sts_one(pw + 1, p.hi());
+                    e1[v] = T(-1); e2[v] = T(0);
+                    if (MODE == SWEEP_INVERSE) p.clear();
+                } else if (v == b) {                               // T_bb (the lo half is above the diagonal: unused)
+                    PR &p = ap[ipn][sc2];
+                    sts_one(pw + 2, p.hi());
+                    e1[v] = T(0); e2[v] = T(-1);
+                    if (MODE == SWEEP_INVERSE) p.clear();
+                } else {                                           // WPN == 0, v = 2, 3: rows of the next pair, columns a, b
+                    const PR &p1 = ap[2 * GRN + 1][sc1], &p2 = ap[2 * GRN + 1][sc2];
+                    e1[v] = (v == 2) ? p1.lo() : p1.hi();
+                    e2[v] = (v == 2) ? p2.lo() : p2.hi();
+                }
+            }
+            if (WPN == 0 && MODE == SWEEP_INVERSE) { ap[2 * GRN + 1][sc1].clear(); ap[2 * GRN + 1][sc2].clear(); }
+            #pragma unroll
+            for (int v = 0; v < 4; ++v) { sts_one(z1 + 4 * qn + v, e1[v]); sts_one(z2 + 4 * qn + v, e2[v]); }
+        }
+        if (MODE == SWEEP_GP) {                                    // the lanes holding rows k1, k2 of the right-hand sides
+            #pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int cb = e * SG::H + ipn;                    // static
+                if (tj == cb % TC) { sts_one(pw + 4 + e, rhs[cb / TC].lo()); sts_one(pw + 6 + e, rhs[cb / TC].hi()); }
+            }
+        }
+    }
+}
+
+template <typename T, int N, int TR, int TC, int MODE, int S, int WP, int GRN, int HCN, int WPN, bool HAS_NEXT>
+__device__ __forceinline__ void sweep2_step(Pair2<T> (&ap)[N / TR / 2][N / TC], Pair2<T> (&rhs)[SweepGeo<N, TR, TC>::NC],
+                                            const T *zc, T *zn, int ti, int tj, int qn, T &dmin, T &d, T &acc_m, T &acc_q) {
+    using SG = SweepGeo<N, TR, TC>;
+    using PR = Pair2<T>;
+    constexpr int sc1n = 4 * HCN + 2 * WPN, sc2n = sc1n + 1, ipn = (4 * GRN + 2 * WPN) / 2;
+    const T *z1 = zc, *z2 = zc + N, *pw = zc + 2 * N;
+    const T d1 = -pw[0], o = -pw[1], d2 = -pw[2];
+    const T det = fma(d1, d2, -o * o);                             // d1 > 0 and det > 0  <=>  both pivots positive
+    d = det;
+    dmin = dev_min(dmin, dev_min(d1, det));
+    const T rdet = dev_rcp_fast<T>(det);
+    const T w11 = d2 * rdet, w12 = -o * rdet, w22 = d1 * rdet;     // W = D^-1
+    PR x1[SG::H], x2[SG::H];
+    T y1[SG::SC], y2[SG::SC];
+    #pragma unroll
+    for (int g = 0; g < SG::NGR; ++g) {
+        if (MODE == SWEEP_GP && SG::pair_dead2(2 * g + 1, S, WP)) continue;   // the whole group is dead
+        T a0, a1, a2, a3, b0, b1, b2, b3;
+        ld4(z1 + 4 * (TR * g + ti), a0, a1, a2, a3);
+        ld4(z2 + 4 * (TR * g + ti), b0, b1, b2, b3);
+        #pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+            const PR za = hh ? PR::make(a2, a3) : PR::make(a0, a1);
+            const PR zb = hh ? PR::make(b2, b3) : PR::make(b0, b1);
+            PR u = za; u.scale(w11); u.fma_bcast(zb, w12); x1[2 * g + hh] = u;
+            PR v = za; v.scale(w12); v.fma_bcast(zb, w22); x2[2 * g + hh] = v;
+        }
+    }
+    #pragma unroll
+    for (int h = 0; h < SG::NGC; ++h) {
+        if (MODE == SWEEP_GP && SG::col_dead2(4 * h + 3, S, WP)) continue;
+        ld4(z1 + 4 * (TC * h + tj), y1[4 * h], y1[4 * h + 1], y1[4 * h + 2], y1[4 * h + 3]);
+        ld4(z2 + 4 * (TC * h + tj), y2[4 * h], y2[4 * h + 1], y2[4 * h + 2], y2[4 * h + 3]);
+    }
+    if (MODE == SWEEP_GP) {                                        // u += X u_K ; scalars: u_K^T W v_K
+        const T u1 = pw[4], v1 = pw[5], u2 = pw[6], v2 = pw[7];
+        const T wu1 = fma(w11, u1, w12 * u2), wu2 = fma(w12, u1, w22 * u2);   // W u_K
+        acc_m = fma(wu1, v1, fma(wu2, v2, acc_m));
+        acc_q = fma(wu1, u1, fma(wu2, u2, acc_q));
+        #pragma unroll
+        for (int j = 0; j < SG::NC; ++j) {
+            const int cb = tj + TC * j;                            // vector cb / H, row pair cb % H of this thread's rows
+            const int ip = cb % SG::H;
+            const int off = 4 * (TR * (ip / 2) + ti) + 2 * (ip % 2);
+            const PR za = PR::make(z1[off], z1[off + 1]), zb = PR::make(z2[off], z2[off + 1]);
+            PR xa = za; xa.scale(w11); xa.fma_bcast(zb, w12);
+            PR xb = za; xb.scale(w12); xb.fma_bcast(zb, w22);
+            const bool first = cb / SG::H == 0;
+            rhs[j].fma_bcast(xa, first ? u1 : v1);
+            rhs[j].fma_bcast(xb, first ? u2 : v2);
+        }
+    }
+    if (HAS_NEXT) {
+        #pragma unroll
+        for (int i = 0; i < SG::H; ++i) {                          // the two column slots of the next pair
+            if (!SG::template skip2<MODE>(i, sc1n, S, WP)) { ap[i][sc1n].fma_bcast(x1[i], y1[sc1n]); ap[i][sc1n].fma_bcast(x2[i], y2[sc1n]); }
+            if (!SG::template skip2<MODE>(i, sc2n, S, WP)) { ap[i][sc2n].fma_bcast(x1[i], y1[sc2n]); ap[i][sc2n].fma_bcast(x2[i], y2[sc2n]); }
+        }
+        #pragma unroll
+        for (int c = 0; c < SG::SC; ++c)                           // the row pair of the next pair
+            if (c != sc1n && c != sc2n && !SG::template skip2<MODE>(ipn, c, S, WP)) {
+                ap[ipn][c].fma_bcast(x1[ipn], y1[c]); ap[ipn][c].fma_bcast(x2[ipn], y2[c]);
+            }
+        sweep2_publish<T, N, TR, TC, MODE, GRN, HCN, WPN>(ap, rhs, zn, ti, tj, qn);
+        tile_sync<SG::LANES>();
+    }
+    #pragma unroll
+    for (int i = 0; i < SG::H; ++i)
+        #pragma unroll
+        for (int c = 0; c < SG::SC; ++c) {
+            if (SG::template skip2<MODE>(i, c, S, WP)) continue;
+            if (HAS_NEXT && (c == sc1n || c == sc2n || i == ipn)) continue;   // done before the publish
+            ap[i][c].fma_bcast(x1[i], y1[c]);
+            ap[i][c].fma_bcast(x2[i], y2[c]);
+        }
+}
+
+// all pivot pairs of level (S, WP), range SUB
+template <typename T, int N, int TR, int TC, int MODE, bool UNROLL, int S, int WP, int SUB>
+__device__ __forceinline__ void sweep2_range(Pair2<T> (&ap)[N / TR / 2][N / TC], Pair2<T> (&rhs)[SweepGeo<N, TR, TC>::NC],
+                                             T *sm, int ti, int tj, T &dmin, T &d, T &acc_m, T &acc_q) {
+    using SG = SweepGeo<N, TR, TC>;
+    constexpr int PM = SG::PMIN;
+    constexpr int Q0 = S * SG::PMAX + SUB * PM;                    // first block of this range
+    constexpr int GR = Q0 / TR, HC = Q0 / TC;
+    constexpr int J0 = ((2 * S + WP) * SG::SUBS + SUB) * PM;       // sequence number of the first pair of this body
+    if (UNROLL) {
+        #pragma unroll
+        for (int t = 0; t < PM - 1; ++t) {
+            const int par = (J0 + t) & 1;
+            sweep2_step<T, N, TR, TC, MODE, S, WP, GR, HC, WP, true>(ap, rhs, sm + par * SG::LINE2, sm + (par ^ 1) * SG::LINE2, ti, tj,
+                                                                     Q0 + t + 1, dmin, d, acc_m, acc_q);
+        }
+    } else {
+        #pragma unroll 1
+        for (int t = 0; t < PM - 1; ++t) {
+            const int par = (J0 + t) & 1;
+            sweep2_step<T, N, TR, TC, MODE, S, WP, GR, HC, WP, true>(ap, rhs, sm + par * SG::LINE2, sm + (par ^ 1) * SG::LINE2, ti, tj,
+                                                                     Q0 + t + 1, dmin, d, acc_m, acc_q);
+        }
+    }
+    constexpr int par = (J0 + PM - 1) & 1;
+    constexpr bool last = (S == SG::NS - 1) && (WP == 1) && (SUB == SG::SUBS - 1);
+    constexpr int SUBN = (SUB + 1 < SG::SUBS) ? SUB + 1 : 0;
+    constexpr int WPN = (SUBN != 0) ? WP : (WP == 1 ? 0 : 1);
+    constexpr int SN = (SUBN != 0 || WP != 1) ? S : S + 1;
+    constexpr int QN = last ? 0 : SN * SG::PMAX + SUBN * PM;
+    sweep2_step<T, N, TR, TC, MODE, S, WP, QN / TR, QN / TC, WPN, !last>(ap, rhs, sm + par * SG::LINE2, sm + (par ^ 1) * SG::LINE2, ti, tj,
+                                                                        QN, dmin, d, acc_m, acc_q);
+}
+
+template <typename T, int N, int TR, int TC, int MODE, bool UNROLL, int S, int WP, int SUB>
+struct Sweep2Ranges {
+    static __device__ __forceinline__ void run(Pair2<T> (&ap)[N / TR / 2][N / TC], Pair2<T> (&rhs)[SweepGeo<N, TR, TC>::NC],
+                                               T *sm, int ti, int tj, T &dmin, T &d, T &acc_m, T &acc_q) {
+        using SG = SweepGeo<N, TR, TC>;
+        sweep2_range<T, N, TR, TC, MODE, UNROLL, S, WP, SUB>(ap, rhs, sm, ti, tj, dmin, d, acc_m, acc_q);
+        constexpr int SUBN = (SUB + 1 < SG::SUBS) ? SUB + 1 : 0;
+        constexpr int WPN = (SUBN != 0) ? WP : (WP == 1 ? 0 : 1);
+        constexpr int SN = (SUBN != 0 || WP != 1) ? S : S + 1;
+        if constexpr (SN < SG::NS) Sweep2Ranges<T, N, TR, TC, MODE, UNROLL, SN, WPN, SUBN>::run(ap, rhs, sm, ti, tj, dmin, d, acc_m, acc_q);
+    }
+};
+
+// the whole elimination of one matrix whose tile is loaded: prologue publish + all steps
+template <typename T, int N, int TR, int TC, int MODE, bool UNROLL, int BLK>
+__device__ __forceinline__ void sweep_eliminate(Pair2<T> (&ap)[N / TR / 2][N / TC], Pair2<T> (&rhs)[SweepGeo<N, TR, TC>::NC],
+                                                T *sm, int ti, int tj, T &dmin, T &d, T &acc_m, T &acc_q) {
+    using SG = SweepGeo<N, TR, TC>;
+    if constexpr (BLK == 2) {
+        sweep2_publish<T, N, TR, TC, MODE, 0, 0, 0>(ap, rhs, sm, ti, tj, 0);
+        tile_sync<SG::LANES>();
+        Sweep2Ranges<T, N, TR, TC, MODE, UNROLL, 0, 0, 0>::run(ap, rhs, sm, ti, tj, dmin, d, acc_m, acc_q);
+    } else {
+        sweep_publish<T, N, TR, TC, MODE, 0, 0, 0>(ap, rhs, sm, ti, tj, 0);
+        tile_sync<SG::LANES>();
+        SweepRanges<T, N, TR, TC, MODE, UNROLL, 0, 0, 0>::run(ap, rhs, sm, ti, tj, dmin, d, acc_m, acc_q);
+    }
+}
+
 // Padded tiers (PadIO): the logical-lower positions of the tile from the UPPER triangle of a column-major
 // n x n matrix (lda = n, n <= N), identity outside; and the store of the leading n x n part of the result.
 template <typename T, int N, int TR, int TC>
@@ -336,7 +572,7 @@ __device__ __forceinline__ void tile_load_upper_padded(T (&a)[N / TR][N / TC], c
         }
 }
 
-template <typename T, int N, int TR, int TC, bool UNROLL, typename IO, int MINB>
+template <typename T, int N, int TR, int TC, bool UNROLL, typename IO, int MINB, int BLK = 1>
 __global__ void __launch_bounds__((SweepGeo<N, TR, TC>::BLOCK), MINB)
 sweep_spd_kernel(IO io, i64 batch, int *__restrict__ info) {
     using SG = SweepGeo<N, TR, TC>;
@@ -359,7 +595,7 @@ sweep_spd_kernel(IO io, i64 batch, int *__restrict__ info) {
         ti = (threadIdx.x % SG::LANES) / TC; tj = threadIdx.x % TC;
     }
     const bool lead = (ti == 0 && tj == 0);
-    T *sm = smem + grp * SG::WORDS;
+    T *sm = smem + grp * (BLK == 2 ? SG::WORDS2 : SG::WORDS);
 
     #pragma unroll 1
     for (i64 base = (i64)blockIdx.x * SG::MPB; base < batch; base += (i64)gridDim.x * SG::MPB) {
@@ -390,9 +626,7 @@ sweep_spd_kernel(IO io, i64 batch, int *__restrict__ info) {
         T dmin = T(1), d = T(1);                                   // smallest pivot so far / current pivot
         T acc_m = T(0), acc_q = T(0);
         PR rhs[SG::NC];                                            // unused in this mode
-        sweep_publish<T, N, TR, TC, SWEEP_INVERSE, 0, 0, 0>(ap, rhs, sm, ti, tj, 0);
-        tile_sync<SG::LANES>();
-        SweepRanges<T, N, TR, TC, SWEEP_INVERSE, UNROLL, 0, 0, 0>::run(ap, rhs, sm, ti, tj, dmin, d, acc_m, acc_q);
+        sweep_eliminate<T, N, TR, TC, SWEEP_INVERSE, UNROLL, BLK>(ap, rhs, sm, ti, tj, dmin, d, acc_m, acc_q);
 
         // a NaN pivot turns every later pivot into NaN, so the last one tells; otherwise the minimum does
         const bool bad = valid && (!(dmin > T(0)) || !(d == d));
@@ -484,7 +718,7 @@ sweep_spd_kernel(IO io, i64 batch, int *__restrict__ info) {
 // Nothing but the scalars is written.  scratch: N*N words per matrix slot, used only to recompute
 // LAPACK's natural-order info for a flagged (non-SPD) matrix.
 // ------------------------------------------------------------------------------------------
-template <typename T, int N, int TR, int TC, bool UNROLL, int MINB>
+template <typename T, int N, int TR, int TC, bool UNROLL, int MINB, int BLK = 1>
 __global__ void __launch_bounds__((SweepGeo<N, TR, TC>::BLOCK), MINB)
 sweep_gp_kernel(GpIO<T> io, i64 batch, int *__restrict__ info, T *__restrict__ scratch) {
     using SG = SweepGeo<N, TR, TC>;
@@ -496,7 +730,7 @@ sweep_gp_kernel(GpIO<T> io, i64 batch, int *__restrict__ info, T *__restrict__ s
     const int grp = threadIdx.x / SG::LANES;
     const int ti = (threadIdx.x % SG::LANES) / TC, tj = threadIdx.x % TC;
     const bool lead = (ti == 0 && tj == 0);
-    T *sm = smem + grp * SG::WORDS;
+    T *sm = smem + grp * (BLK == 2 ? SG::WORDS2 : SG::WORDS);
 
     #pragma unroll 1
     for (i64 base = (i64)blockIdx.x * SG::MPB; base < batch; base += (i64)gridDim.x * SG::MPB) {
@@ -541,9 +775,7 @@ sweep_gp_kernel(GpIO<T> io, i64 batch, int *__restrict__ info, T *__restrict__ s
         }
 
         T dmin = T(1), d = T(1), acc_m = T(0), acc_q = T(0);
-        sweep_publish<T, N, TR, TC, SWEEP_GP, 0, 0, 0>(ap, rhs, sm, ti, tj, 0);
-        tile_sync<SG::LANES>();
-        SweepRanges<T, N, TR, TC, SWEEP_GP, UNROLL, 0, 0, 0>::run(ap, rhs, sm, ti, tj, dmin, d, acc_m, acc_q);
+        sweep_eliminate<T, N, TR, TC, SWEEP_GP, UNROLL, BLK>(ap, rhs, sm, ti, tj, dmin, d, acc_m, acc_q);
 
         const bool bad = valid && (!(dmin > T(0)) || !(d == d));
         if (!valid || !lead) continue;
@@ -564,6 +796,206 @@ sweep_gp_kernel(GpIO<T> io, i64 batch, int *__restrict__ info, T *__restrict__ s
         if (io.variances) io.variances[m] = io.e[m] - acc_q;
         if (info) info[m] = 0;
     }
+}
+
+// ==========================================================================================
+// TMA tile I/O for the warp tiers whose matrix columns are exactly one 128-byte line (n = 32 fp32,
+// n = 16 fp64): the global side of the kernel leaves the LSU pipe.
+//
+// ncu on the direct-access kernel (profiles/r1_sweep32_summary.md): the LSU data pipe is the busiest unit
+// (67 %), and 40 % of its wavefronts are the 16-byte global loads / stores of the four matrices that share
+// a warp (16 distinct lines per instruction).  Here one lane issues ONE `cp.async.bulk.tensor.2d` per
+// warp tile: the batch is described to the TMA unit as a 2-D tensor [N rows x (N batch) columns], the box
+// is the warp's MPW consecutive matrices, and the 128-byte swizzle mode (16-byte chunk index XOR column
+// mod 8) makes the tile reads (transposed twins of the upper triangle) and the mirrored stores of the
+// 2 x 4 lane grid bank-conflict free; the natural-position stores are 2-way.  Results go back with one
+// `cp.async.bulk.tensor` store per warp tile (columns beyond the batch are clipped by the tensor map,
+// loads of them are zero-filled), so the tail needs no special code.  Sequence per warp and tile:
+//   wait(mbarrier) -> registers <- smem -> eliminate -> smem <- registers -> fence.proxy.async ->
+//   bulk store -> wait_group.read -> arm mbarrier + bulk load of the next tile.
+// All mbarrier waits are bounded and trap instead of hanging.
+// ==========================================================================================
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long *bar, unsigned parity) {
+    unsigned ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    unsigned spins = 0;
+    while (!mbar_try_wait(bar, parity))
+        if (++spins > (1u << 22)) __trap();                        // a lost transaction must not hang the GPU
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const void *tmap, int c0, int c1, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const void *tmap, int c0, int c1, const void *src) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];"
+                 ::"l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(src)) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit_and_wait_read() {
+    asm volatile("cp.async.bulk.commit_group;\n\tcp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+struct TmaMaps {                                                   // two 128-byte CUtensorMap objects, opaque here
+    alignas(64) unsigned char in[128];
+    alignas(64) unsigned char out[128];
+};
+
+template <typename T, int N, int TR, int TC>
+struct SweepTmaGeo {
+    using SG = SweepGeo<N, TR, TC>;
+    static_assert(N * sizeof(T) == 128, "one matrix column must be one 128-byte swizzle line");
+    static_assert(SG::LANES < 32, "warp tiers with several matrices per warp");
+    static constexpr int MPW = 32 / SG::LANES;                     // matrices per warp = per TMA box
+    static constexpr int WARPS = SG::BLOCK / 32;
+    static constexpr int MAT_BYTES = N * N * (int)sizeof(T);
+    static constexpr int BOX_BYTES = MPW * MAT_BYTES;
+    static constexpr size_t SMEM = (size_t)WARPS * BOX_BYTES + (size_t)SG::MPB * SG::WORDS * sizeof(T) + WARPS * 8;
+    // byte offset of the 16-byte chunk `chunk` of column `col` inside a (1024-byte aligned) swizzled matrix buffer
+    static __device__ __forceinline__ int off(int chunk, int col) { return col * 128 + ((chunk ^ (col & 7)) << 4); }
+};
+
+template <typename T, int N, int TR, int TC, bool UNROLL, int MINB>
+__global__ void __launch_bounds__((SweepGeo<N, TR, TC>::BLOCK), MINB)
+sweep_spd_tma_kernel(const __grid_constant__ TmaMaps maps, const T *__restrict__ in, i64 in_stride, T *__restrict__ out, i64 out_stride,
+                     i64 batch, int *__restrict__ info) {
+    using SG = SweepGeo<N, TR, TC>;
+    using TG = SweepTmaGeo<T, N, TR, TC>;
+    using PR = Pair2<T>;
+    constexpr int SR = SG::SR, SC = SG::SC, H = SG::H;
+    constexpr int CH = 16 / (int)sizeof(T);                        // elements per 16-byte chunk (= 4 for fp32)
+    static_assert(CH == 4, "the tile code assumes 4-element chunks");
+    extern __shared__ __align__(1024) unsigned char smem_raw_tma[];   // 128-byte swizzle repeats every 1024 bytes
+    unsigned char *base = smem_raw_tma;
+    const int warp = threadIdx.x >> 5, wl = threadIdx.x & 31;
+    const int mat = wl / SG::LANES, lane = wl % SG::LANES;
+    const int ti = lane / TC, tj = lane % TC;
+    const bool lead = (ti == 0 && tj == 0);
+    unsigned char *box = base + (size_t)warp * TG::BOX_BYTES;      // this warp's MPW matrices
+    unsigned char *buf = box + (size_t)mat * TG::MAT_BYTES;        // this thread's matrix
+    T *lines = reinterpret_cast<T *>(base + (size_t)TG::WARPS * TG::BOX_BYTES);
+    T *sm = lines + (size_t)(warp * TG::MPW + mat) * SG::WORDS;
+    unsigned long long *bar = reinterpret_cast<unsigned long long *>(lines + (size_t)SG::MPB * SG::WORDS) + warp;
+
+    if ((smem_u32(base) & 1023u) != 0) __trap();                   // the swizzle pattern is defined on 1024-byte aligned addresses
+    if (wl == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const i64 ntiles = (batch + TG::MPW - 1) / TG::MPW;
+    const i64 tstride = (i64)gridDim.x * TG::WARPS;
+    i64 tile = (i64)blockIdx.x * TG::WARPS + warp;
+    unsigned phase = 0;
+    if (tile < ntiles && wl == 0) {
+        mbar_expect_tx(bar, TG::BOX_BYTES);
+        tma_load_2d(box, &maps.in, 0, (int)(tile * TG::MPW * N), bar);
+    }
+    #pragma unroll 1
+    for (; tile < ntiles; tile += tstride) {
+        const i64 m = tile * TG::MPW + mat;
+        const bool valid = m < batch;
+        mbar_wait(bar, phase);
+        phase ^= 1;
+
+        PR ap[H][SC];
+        {
+            T a[SR][SC];
+            #pragma unroll
+            for (int g = 0; g < SG::NGR; ++g)
+                #pragma unroll
+                for (int h = 0; h < SG::NGC; ++h) {
+                    const int br = TR * g + ti, bc = TC * h + tj;
+                    #pragma unroll
+                    for (int p = 0; p < 4; ++p) {
+                        // lower block (br >= bc): its transposed twin from the UPPER triangle: column 4 br + p, rows 4 bc ..
+                        if (!SG::upper(2 * g, 4 * h) && br >= bc)
+                            ld4(reinterpret_cast<const T *>(buf + TG::off(bc, 4 * br + p)), a[4 * g + p][4 * h], a[4 * g + p][4 * h + 1],
+                                a[4 * g + p][4 * h + 2], a[4 * g + p][4 * h + 3]);
+                        else { a[4 * g + p][4 * h] = T(0); a[4 * g + p][4 * h + 1] = T(0); a[4 * g + p][4 * h + 2] = T(0); a[4 * g + p][4 * h + 3] = T(0); }
+                    }
+                }
+            #pragma unroll
+            for (int i = 0; i < H; ++i)
+                #pragma unroll
+                for (int c = 0; c < SC; ++c) ap[i][c] = PR::make(-a[2 * i][c], -a[2 * i + 1][c]);
+        }
+        __syncwarp();                                              // everybody has its tile: the box may be overwritten
+
+        T dmin = T(1), d = T(1), acc_m = T(0), acc_q = T(0);
+        PR rhs[SG::NC];
+        sweep_eliminate<T, N, TR, TC, SWEEP_INVERSE, UNROLL, 1>(ap, rhs, sm, ti, tj, dmin, d, acc_m, acc_q);
+
+        const bool bad = valid && (!(dmin > T(0)) || !(d == d));
+        int st = 0;
+        if (__any_sync(0xffffffffu, bad)) {                        // rare: LAPACK's natural-order index; global output as scratch
+            if (bad && lead) {
+                st = exact_potrf_info<T>(in + m * in_stride, out + m * out_stride, N);
+                if (st == 0) st = N;
+            }
+            fence_proxy_async();                                   // scratch writes are ordered before the bulk store below
+            __syncwarp();
+        }
+        if (valid && lead && info) info[m] = st;
+        // ---- result -> swizzled box (both triangles; NaN for a flagged matrix)
+        #pragma unroll
+        for (int g = 0; g < SG::NGR; ++g) {
+            #pragma unroll
+            for (int h = 0; h < SG::NGC; ++h) {
+                const int br = TR * g + ti, bc = TC * h + tj;
+                if (bad) {
+                    #pragma unroll
+                    for (int v = 0; v < 4; ++v)
+                        st4(reinterpret_cast<T *>(buf + TG::off(br, 4 * bc + v)), dev_nan<T>(), dev_nan<T>(), dev_nan<T>(), dev_nan<T>());
+                    continue;
+                }
+                if (SG::upper(2 * g, 4 * h)) continue;
+                T b[4][4];
+                #pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    b[0][v] = ap[2 * g][4 * h + v].lo(); b[1][v] = ap[2 * g][4 * h + v].hi();
+                    b[2][v] = ap[2 * g + 1][4 * h + v].lo(); b[3][v] = ap[2 * g + 1][4 * h + v].hi();
+                }
+                if (br == bc) {
+                    #pragma unroll
+                    for (int v = 0; v < 4; ++v)
+                        st4(reinterpret_cast<T *>(buf + TG::off(br, 4 * bc + v)), v <= 0 ? b[0][v] : b[v][0], v <= 1 ? b[1][v] : b[v][1],
+                            v <= 2 ? b[2][v] : b[v][2], b[3][v]);
+                } else if (br > bc) {
+                    #pragma unroll
+                    for (int v = 0; v < 4; ++v)
+                        st4(reinterpret_cast<T *>(buf + TG::off(br, 4 * bc + v)), b[0][v], b[1][v], b[2][v], b[3][v]);
+                    #pragma unroll
+                    for (int ww = 0; ww < 4; ++ww)
+                        st4(reinterpret_cast<T *>(buf + TG::off(bc, 4 * br + ww)), b[ww][0], b[ww][1], b[ww][2], b[ww][3]);
+                }
+            }
+        }
+        fence_proxy_async();                                       // generic-proxy writes -> visible to the TMA unit
+        __syncwarp();
+        if (wl == 0) {
+            tma_store_2d(&maps.out, 0, (int)(tile * TG::MPW * N), box);
+            tma_store_commit_and_wait_read();                      // the box has been read: it can take the next tile
+            if (tile + tstride < ntiles) {
+                mbar_expect_tx(bar, TG::BOX_BYTES);
+                tma_load_2d(box, &maps.in, 0, (int)((tile + tstride) * TG::MPW * N), bar);
+            }
+        }
+        __syncwarp();
+    }
+    if (wl == 0) tma_store_wait_all();                             // global writes complete before the CTA retires
 }
 
 }  // namespace invgpu

@@ -65,24 +65,35 @@
 #define INVGPU_ONESWEEP_F64(X) X(double, 8, 1, 1, true, 2) X(double, 16, 2, 2, false, 2) X(double, 32, 4, 4, false, 2)
 #define INVGPU_ONESWEEP_ALL(X) INVGPU_ONESWEEP_F32(X) INVGPU_ONESWEEP_F64(X)
 
-// SPD inverse, look-ahead sweep kernel (sweep_kernels.cuh):  X(V, T, N, TR, TC, UNROLL, MINB)
+// SPD inverse, look-ahead sweep kernel (sweep_kernels.cuh):  X(V, T, N, TR, TC, UNROLL, MINB, BLK)
 // V = variant number; V == 0 is what the dispatcher uses, the others are reachable with
-// INVGPU_SWEEP_VARIANT=V (tools/kbench.py experiments).
+// INVGPU_SWEEP_VARIANT=V (tools/kbench.py experiments).  BLK = 1: scalar pivots, 2: 2x2 block pivots.
 #define INVGPU_SWEEP_F32(X)                                                                     \
-    X(0, float, 16, 2, 2, false, 4) X(1, float, 16, 1, 2, false, 3)                             \
-    X(0, float, 32, 2, 4, false, 3) X(1, float, 32, 4, 2, false, 3) X(2, float, 32, 4, 4, false, 5) X(3, float, 32, 2, 4, true, 3) \
-    X(0, float, 64, 4, 8, false, 3) X(1, float, 64, 8, 8, false, 8) X(2, float, 64, 4, 8, true, 3) X(3, float, 64, 8, 4, false, 3) \
-    X(0, float, 128, 8, 16, false, 3) X(1, float, 128, 16, 16, false, 2) X(2, float, 128, 8, 16, true, 3) X(3, float, 128, 16, 8, false, 3)
+    X(0, float, 16, 2, 2, false, 4, 1)                                                          \
+    X(0, float, 32, 2, 4, false, 3, 1) X(1, float, 32, 4, 2, false, 3, 1) X(4, float, 32, 2, 4, false, 3, 2) \
+    X(0, float, 64, 8, 4, false, 3, 1) X(3, float, 64, 4, 8, false, 3, 1) X(4, float, 64, 8, 4, false, 3, 2) \
+    X(0, float, 128, 16, 8, false, 3, 1) X(3, float, 128, 8, 16, false, 3, 1) X(4, float, 128, 16, 8, false, 3, 2)
 #define INVGPU_SWEEP_F64(X)                                                                     \
-    X(0, double, 16, 2, 2, false, 2) X(0, double, 32, 4, 4, false, 2) X(0, double, 64, 8, 8, false, 4) X(0, double, 128, 16, 16, false, 1)
+    X(0, double, 16, 2, 2, false, 2, 1) X(0, double, 32, 4, 4, false, 2, 1) X(0, double, 64, 8, 8, false, 4, 1) X(0, double, 128, 16, 16, false, 1, 1) \
+    X(4, double, 64, 8, 8, false, 4, 2) X(4, double, 128, 16, 16, false, 1, 2)
+// Measured on B200, fraction of the HBM roofline (tools/kbench.py, gpurun_out/o_kbench.log), BLK = 1 vs BLK = 2:
+//   fp32 n = 32: 0.51 vs 0.44   64: 0.28 vs 0.25   128: 0.18 vs 0.165   fp64 64: 0.229 vs 0.232   128: 0.112 vs 0.116
+// The 2x2 block pivots halve barriers and dependency chains but double the live operand registers (x1, x2, y1, y2)
+// and the shared-memory bytes per step; the kernels are not chain-bound enough for that to pay.  Thread grids:
+// wide tiles (TR > TC) win by 3-7 % at n = 64 / 128 (row owners of a pivot sit in one quarter-warp).
 #define INVGPU_SWEEP_ALL(X) INVGPU_SWEEP_F32(X) INVGPU_SWEEP_F64(X)
 
-// fused GP mean / variance on the sweep machinery (sweep_gp_kernel):  X(T, N, TR, TC, UNROLL, MINB)
+// the same kernel with TMA tile I/O (sweep_spd_tma_kernel; columns of exactly 128 bytes):  X(V, T, N, TR, TC, UNROLL, MINB)
+#define INVGPU_SWEEP_TMA_F32(X) X(6, float, 32, 2, 4, false, 3) X(7, float, 32, 4, 2, false, 3)
+#define INVGPU_SWEEP_TMA_F64(X)
+#define INVGPU_SWEEP_TMA_ALL(X) INVGPU_SWEEP_TMA_F32(X) INVGPU_SWEEP_TMA_F64(X)
+
+// fused GP mean / variance on the sweep machinery (sweep_gp_kernel):  X(V, T, N, TR, TC, UNROLL, MINB, BLK)
 // Measured on B200 against the three-phase tile kernels above (fraction of the HBM roofline, sweep vs tile):
 // fp32 n = 32: 0.45 vs 0.57, 64: 0.23 vs 0.39, 128: 0.118 vs 0.092; fp64 32/64/128: equal within 5 %.
 // Only the CTA tier gains (one barrier per pivot instead of the rolled potrf's per-pivot chain), so only
-// that one is dispatched; the warp tiers stay on the fully unrolled tile kernels with exact static pruning.
-#define INVGPU_SWEEP_GP_F32(X) X(float, 128, 8, 16, false, 3)
+// that one is dispatched (16 x 8 threads with 2x2 block pivots: 0.123; 8 x 16 scalar pivots: 0.118); the warp tiers stay on the fully unrolled tile kernels with exact static pruning.
+#define INVGPU_SWEEP_GP_F32(X) X(0, float, 128, 16, 8, false, 3, 2) X(3, float, 128, 8, 16, false, 3, 1)
 #define INVGPU_SWEEP_GP_F64(X)
 #define INVGPU_SWEEP_GP_ALL(X) INVGPU_SWEEP_GP_F32(X) INVGPU_SWEEP_GP_F64(X)
 

@@ -19,18 +19,27 @@ int launch_gj(IO io, int n, i64 batch, int *dInfo, cudaStream_t st, DeviceState 
 template <typename T, int N, int TR, int TC, bool STAGE, int MINB>
 int launch_onesweep(StridedIO<T> io, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds);
 
-template <typename T, int N, int TR, int TC, bool UNROLL, int MINB>
+template <typename T, int N, int TR, int TC, bool UNROLL, int MINB, int BLK>
 int launch_sweep(StridedIO<T> io, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds);
 
-template <typename T, int N, int TR, int TC, bool UNROLL, int MINB>
+template <typename T, int N, int TR, int TC, bool UNROLL, int MINB, int BLK>
 int launch_sweep_gp(GpIO<T> io, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds);
 
 template <typename T, int N, int TR, int TC, int MINB>
 int launch_sweep_pad(PadIO<T> io, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds);
 
+// returns INVGPU_TMA_UNAVAILABLE when the batch cannot be described to the TMA unit (strides, size, driver)
+#define INVGPU_TMA_UNAVAILABLE (-1001)
+template <typename T, int N, int TR, int TC, bool UNROLL, int MINB>
+int launch_sweep_tma(StridedIO<T> io, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds);
+
 }  // namespace invgpu
 
 #ifdef INVGPU_TILE_DEFINE
+#include <cuda.h>
+#include <string.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include "tile_kernels.cuh"
 #include "gj_kernels.cuh"
 #include "onesweep_kernels.cuh"
@@ -38,11 +47,11 @@ int launch_sweep_pad(PadIO<T> io, i64 batch, int *dInfo, cudaStream_t st, Device
 
 namespace invgpu {
 
-template <typename T, int N, int TR, int TC, bool UNROLL, int MINB>
+template <typename T, int N, int TR, int TC, bool UNROLL, int MINB, int BLK>
 int launch_sweep(StridedIO<T> io, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds) {
     using SG = SweepGeo<N, TR, TC>;
-    auto kern = sweep_spd_kernel<T, N, TR, TC, UNROLL, StridedIO<T>, MINB>;
-    const size_t smem = (size_t)SG::MPB * SG::WORDS * sizeof(T);
+    auto kern = sweep_spd_kernel<T, N, TR, TC, UNROLL, StridedIO<T>, MINB, BLK>;
+    const size_t smem = (size_t)SG::MPB * (BLK == 2 ? SG::WORDS2 : SG::WORDS) * sizeof(T);
     int grid = 0;
     int rc = persistent_grid(kern, SG::BLOCK, smem, (batch + SG::MPB - 1) / SG::MPB, ds, &grid);
     if (rc) return rc;
@@ -64,6 +73,65 @@ int launch_sweep_pad(PadIO<T> io, i64 batch, int *dInfo, cudaStream_t st, Device
     return (int)cudaGetLastError();
 }
 
+// ---- TMA descriptors: cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda at link time)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// the batch as a 2-D tensor [N rows (contiguous) x N*batch columns], box = `mats` whole matrices, 128-byte swizzle
+template <typename T, int N>
+static int make_batch_tensor_map(void *out128, const T *base, i64 batch, int mats) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return INVGPU_TMA_UNAVAILABLE;
+    static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap is 128 bytes");
+    const cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)N * (cuuint64_t)batch};
+    const cuuint64_t strides[1] = {(cuuint64_t)N * sizeof(T)};
+    const cuuint32_t box[2] = {(cuuint32_t)N, (cuuint32_t)(N * mats)};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUtensorMapDataType dt = sizeof(T) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64;
+    CUtensorMap m;
+    const CUresult r = enc(&m, dt, 2, const_cast<T *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return INVGPU_TMA_UNAVAILABLE;
+    memcpy(out128, &m, 128);
+    return 0;
+}
+
+template <typename T, int N, int TR, int TC, bool UNROLL, int MINB>
+int launch_sweep_tma(StridedIO<T> io, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds) {
+    using SG = SweepGeo<N, TR, TC>;
+    using TG = SweepTmaGeo<T, N, TR, TC>;
+    if (io.in_stride != (i64)N * N || io.out_stride != (i64)N * N) return INVGPU_TMA_UNAVAILABLE;   // columns must be equidistant
+    if ((i64)N * batch > 0x7fffffffLL || TG::MPW * N > 256) return INVGPU_TMA_UNAVAILABLE;          // 32-bit box coordinates
+    TmaMaps maps;
+    int rc = make_batch_tensor_map<T, N>(maps.in, io.in, batch, TG::MPW);
+    if (rc) return rc;
+    rc = make_batch_tensor_map<T, N>(maps.out, io.out, batch, TG::MPW);
+    if (rc) return rc;
+    auto kern = sweep_spd_tma_kernel<T, N, TR, TC, UNROLL, MINB>;
+    int grid = 0;
+    rc = persistent_grid(kern, SG::BLOCK, TG::SMEM, (batch + SG::MPB - 1) / SG::MPB, ds, &grid);
+    if (rc) return rc;
+    static int trace = -1;
+    if (trace < 0) { const char *e = getenv("INVGPU_TRACE"); trace = (e && atoi(e) > 0) ? 1 : 0; }
+    if (trace) fprintf(stderr, "[invgpu] sweep_spd_tma_kernel<n=%d, %dx%d> grid %d smem %zu\n", N, TR, TC, grid, (size_t)TG::SMEM);
+    kern<<<grid, SG::BLOCK, TG::SMEM, st>>>(maps, io.in, io.in_stride, io.out, io.out_stride, batch, dInfo);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return (int)cudaGetLastError();
+}
+
 // scratch for the (rare) natural-order info recomputation of flagged GP matrices
 static int ensure_gp_scratch(DeviceState *ds, size_t need) {
     if (ds->gp_scratch_bytes < need) {
@@ -79,11 +147,11 @@ static int ensure_gp_scratch(DeviceState *ds, size_t need) {
     return 0;
 }
 
-template <typename T, int N, int TR, int TC, bool UNROLL, int MINB>
+template <typename T, int N, int TR, int TC, bool UNROLL, int MINB, int BLK>
 int launch_sweep_gp(GpIO<T> io, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds) {
     using SG = SweepGeo<N, TR, TC>;
-    auto kern = sweep_gp_kernel<T, N, TR, TC, UNROLL, MINB>;
-    const size_t smem = (size_t)SG::MPB * SG::WORDS * sizeof(T);
+    auto kern = sweep_gp_kernel<T, N, TR, TC, UNROLL, MINB, BLK>;
+    const size_t smem = (size_t)SG::MPB * (BLK == 2 ? SG::WORDS2 : SG::WORDS) * sizeof(T);
     int grid = 0;
     int rc = persistent_grid(kern, SG::BLOCK, smem, (batch + SG::MPB - 1) / SG::MPB, ds, &grid);
     if (rc) return rc;
@@ -159,12 +227,14 @@ int launch_tile_gp(GpIO<T> io, i64 batch, int *dInfo, cudaStream_t st, DeviceSta
     template int invgpu::launch_gj<T, N, ROWS, invgpu::PtrIO<T>, MINB>(invgpu::PtrIO<T>, int, invgpu::i64, int *, cudaStream_t, invgpu::DeviceState *);
 #define INVGPU_ONESWEEP_INSTANTIATE(T, N, TR, TC, STAGE, MINB) \
     template int invgpu::launch_onesweep<T, N, TR, TC, STAGE, MINB>(invgpu::StridedIO<T>, invgpu::i64, int *, cudaStream_t, invgpu::DeviceState *);
+#define INVGPU_SWEEP_TMA_INSTANTIATE(V, T, N, TR, TC, UNROLL, MINB) \
+    template int invgpu::launch_sweep_tma<T, N, TR, TC, UNROLL, MINB>(invgpu::StridedIO<T>, invgpu::i64, int *, cudaStream_t, invgpu::DeviceState *);
 #define INVGPU_SWEEP_PAD_INSTANTIATE(T, N, TR, TC, MINB) \
     template int invgpu::launch_sweep_pad<T, N, TR, TC, MINB>(invgpu::PadIO<T>, invgpu::i64, int *, cudaStream_t, invgpu::DeviceState *);
-#define INVGPU_SWEEP_GP_INSTANTIATE(T, N, TR, TC, UNROLL, MINB) \
-    template int invgpu::launch_sweep_gp<T, N, TR, TC, UNROLL, MINB>(invgpu::GpIO<T>, invgpu::i64, int *, cudaStream_t, invgpu::DeviceState *);
-#define INVGPU_SWEEP_INSTANTIATE(V, T, N, TR, TC, UNROLL, MINB) \
-    template int invgpu::launch_sweep<T, N, TR, TC, UNROLL, MINB>(invgpu::StridedIO<T>, invgpu::i64, int *, cudaStream_t, invgpu::DeviceState *);
+#define INVGPU_SWEEP_GP_INSTANTIATE(V, T, N, TR, TC, UNROLL, MINB, BLK) \
+    template int invgpu::launch_sweep_gp<T, N, TR, TC, UNROLL, MINB, BLK>(invgpu::GpIO<T>, invgpu::i64, int *, cudaStream_t, invgpu::DeviceState *);
+#define INVGPU_SWEEP_INSTANTIATE(V, T, N, TR, TC, UNROLL, MINB, BLK) \
+    template int invgpu::launch_sweep<T, N, TR, TC, UNROLL, MINB, BLK>(invgpu::StridedIO<T>, invgpu::i64, int *, cudaStream_t, invgpu::DeviceState *);
 #define INVGPU_TILE_INSTANTIATE_GP(T, N, TR, TC, MINB) \
     template int invgpu::launch_tile_gp<T, N, TR, TC, MINB>(invgpu::GpIO<T>, invgpu::i64, int *, cudaStream_t, invgpu::DeviceState *);
 #endif

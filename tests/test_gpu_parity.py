@@ -532,3 +532,45 @@ def test_full_size_gp_25k_128(api, torch):
     x = torch.linalg.solve(mm, d[idx].double().unsqueeze(-1)).squeeze(-1)
     ref = (a[idx].double() * x).sum(-1)
     assert float((means[idx].double() - ref).abs().max()) <= 1e-4
+
+
+# --------------------------------------------------------------------------------------- kernel variants
+_VARIANT_SNIPPET = r"""
+import sys, numpy as np
+sys.path.insert(0, {root!r})
+import oracle as orc
+from cuda_matrix_inversion_b200 import api
+n, batch = {n}, {batch}
+rng = np.random.default_rng(5)
+r = rng.random((batch, n, n))
+a = (r + r.transpose(0, 2, 1) + n * np.eye(n)).astype(np.float32)
+a[3] = -np.eye(n)                                   # flagged: info 1
+a[batch - 2, n - 1, n - 1] = -5.0                   # flagged in the last (partial) warp tile: info n
+flat = orc.to_colmajor(a)
+got, info = api.spd_inverse_host(flat, n)
+want, oinfo = orc.chol_inverse(flat, n)
+assert (info == oinfo).all(), (info[info != oinfo], oinfo[info != oinfo])
+good = info == 0
+g, w = orc.from_colmajor(got, n), orc.from_colmajor(want, n)
+err = np.abs(g[good] - w[good]).max() / np.abs(w[good]).max()
+assert err <= 1e-4, err
+assert np.isnan(g[~good]).all() and (~good).sum() == 2
+print("variant ok", err)
+"""
+
+
+@pytest.mark.parametrize("variant,n", [(6, 32), (7, 32), (4, 32), (4, 64), (4, 128), (1, 32), (3, 64), (3, 128)])
+def test_sweep_kernel_variants(variant, n):
+    """The non-default sweep configurations (TMA tile I/O: 6, 7; 2x2 block pivots: 4; other thread grids) are selected
+    per process with INVGPU_SWEEP_VARIANT, so each runs in a child process: oracle parity, flags, ragged tail."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, INVGPU_SWEEP_VARIANT=str(variant), INVGPU_TRACE="1")
+    batch = 1027 if n <= 32 else 131
+    p = subprocess.run([sys.executable, "-c", _VARIANT_SNIPPET.format(root=root, n=n, batch=batch)], env=env,
+                       capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert "variant ok" in p.stdout
+    if variant in (6, 7):
+        assert "sweep_spd_tma_kernel" in p.stderr      # the TMA kernel really ran (no silent fallback)

@@ -20,8 +20,11 @@ using namespace invgpu;
 #ifndef PMINB
 #define PMINB 3
 #endif
+#ifndef PBLK
+#define PBLK 1
+#endif
 #ifdef PGP
-template __global__ void invgpu::sweep_gp_kernel<PT, PN, PTR, PTC, PUNROLL, PMINB>(GpIO<PT>, i64, int *, PT *);
+template __global__ void invgpu::sweep_gp_kernel<PT, PN, PTR, PTC, PUNROLL, PMINB, PBLK>(GpIO<PT>, i64, int *, PT *);
 #else
-template __global__ void invgpu::sweep_spd_kernel<PT, PN, PTR, PTC, PUNROLL, StridedIO<PT>, PMINB>(StridedIO<PT>, i64, int *);
+template __global__ void invgpu::sweep_spd_kernel<PT, PN, PTR, PTC, PUNROLL, StridedIO<PT>, PMINB, PBLK>(StridedIO<PT>, i64, int *);
 #endif

@@ -249,7 +249,7 @@ def _extras(torch, api, steps, warmup, hbm_peak):
     ms = float(np.median(t))
     gbs = 2 * 4 * total / (ms * 1e-3) / 1e9
     out["mixed_500k_f32"] = {"matrices_per_s": cnt / (ms * 1e-3), "ms": ms, "algorithmic_GBps": gbs, "hbm_frac": gbs / hbm_peak,
-                             "flagged": int((info != 0).sum()), "tier": "persistent grids over five padded sweep tiers (16/32/64/128/256), counting-sort work lists",
+                             "flagged": int((info != 0).sum()), "tier": "persistent grids over nine padded sweep tiers (16/24/32/48/64/96/128/192/256), counting-sort work lists",
                              "note": "timing includes the host-side planning (~6.5 ms) and work-list upload"}
     return out
 

@@ -159,7 +159,7 @@ static int ensure_pipeline(DeviceState *ds, size_t slot_bytes) {
             INVGPU_TRY(cudaEventCreateWithFlags(&ds->ev_comp[i], cudaEventDisableTiming));
             INVGPU_TRY(cudaEventCreateWithFlags(&ds->ev_out[i], cudaEventDisableTiming));
         }
-        for (int i = 0; i < 5; ++i) INVGPU_TRY(cudaEventCreateWithFlags(&ds->ev_mixed[i], cudaEventDisableTiming));
+        for (int i = 0; i < DeviceState::kMixedTiers; ++i) INVGPU_TRY(cudaEventCreateWithFlags(&ds->ev_mixed[i], cudaEventDisableTiming));
         ds->streams_ready = true;
     }
     if (ds->d_ws_bytes < slot_bytes) {
@@ -352,10 +352,11 @@ static int run_mixed_spd(T *const *hIn, T *const *hOut, const int *hN, i64 count
         ++hist[n];
     }
     // tier b holds n in (lo_b, hi_b]; position of the first item of order n in the concatenated list
-    constexpr int NT = 5;
-    static const int hi[NT] = {16, 32, 64, 128, 256}, lo[NT] = {0, 16, 32, 64, 128};
-    i64 bcount[NT] = {0, 0, 0, 0, 0}, first[257];
-    int nmax[NT] = {1, 1, 1, 1, 1};
+    constexpr int NT = DeviceState::kMixedTiers;
+    static const int hi[NT] = {16, 24, 32, 48, 64, 96, 128, 192, 256}, lo[NT] = {0, 16, 24, 32, 48, 64, 96, 128, 192};
+    i64 bcount[NT], first[257];
+    int nmax[NT];
+    for (int b = 0; b < NT; ++b) { bcount[b] = 0; nmax[b] = 1; }
     {
         i64 pos = 0;
         for (int b = 0; b < NT; ++b)
@@ -367,7 +368,7 @@ static int run_mixed_spd(T *const *hIn, T *const *hOut, const int *hN, i64 count
     std::lock_guard<std::mutex> lk(engine_mutex());
     int rc = ensure_pipeline(ds, 0);                          // streams + events
     if (rc) return rc;
-    constexpr size_t HDR = 128;                               // tickets of the generic kernels
+    constexpr size_t HDR = 256;                               // tickets of the generic kernels
     const size_t need = (size_t)count * sizeof(MixedItem) + HDR;
     if (ds->mixed_bytes < need) {
         if (ds->d_mixed) cudaFree(ds->d_mixed);

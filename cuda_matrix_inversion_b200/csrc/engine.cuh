@@ -36,7 +36,8 @@ struct DeviceState {
     size_t h_ring_bytes = 0;
     cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
     cudaEvent_t ev_in[kSlots], ev_comp[kSlots], ev_out[kSlots];
-    cudaEvent_t ev_mixed[5];                                  // one per tier of the mixed-dimension scheduler
+    static const int kMixedTiers = 9;                         // 16 / 24 / 32 / 48 / 64 / 96 / 128 / 192 / 256
+    cudaEvent_t ev_mixed[kMixedTiers];                        // one per tier of the mixed-dimension scheduler
     bool streams_ready = false;
     // scratch of the fused GP tile kernels (natural-order info recomputation of flagged matrices)
     void *gp_scratch = nullptr;

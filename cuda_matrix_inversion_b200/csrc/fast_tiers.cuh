@@ -11,6 +11,9 @@
 #include "tile_launch.cuh"
 
 #define INVGPU_NO_FAST_PATH (-1000)
+// orders up to this bound stay on the lane = row kernel (gj_kernels.cuh), measured faster there on B200:
+// fp32 n = 16: 0.177 vs 0.147 of the HBM roofline, 32: 0.101 vs 0.074; fp64 32: 0.120 vs 0.138 (tile wins)
+#define INVGPU_GJT_MIN_N(T) (sizeof(T) == 4 ? 32 : 16)
 #ifndef INVGPU_SWEEP_MIN_N
 #define INVGPU_SWEEP_MIN_N 16
 #endif
@@ -100,8 +103,21 @@ template <typename IO, typename TT> struct IOCast;
 template <typename T, typename TT> struct IOCast<StridedIO<T>, TT> { typedef StridedIO<TT> type; };
 template <typename T, typename TT> struct IOCast<PtrIO<T>, TT> { typedef PtrIO<TT> type; };
 
+// 2-D tile Gauss-Jordan: smallest instantiated padded order >= n wins (ascending lists)
+#define INVGPU_GJT_TRY(TT, N, TR, TC, MINB)                                                         \
+    if (std::is_same<T, TT>::value && n <= N)                                                        \
+        return launch_gj_tile<TT, N, TR, TC, typename IOCast<IO, TT>::type, MINB>(                   \
+            *reinterpret_cast<typename IOCast<IO, TT>::type *>(&io), n, batch, dInfo, st, ds);
+
 template <typename T, typename IO>
 static int fast_general(IO io, int n, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds) {
+    static int which = -1;                            // INVGPU_GJ_KERNEL=rowlane | generic: the older tiers (experiments)
+    if (which < 0) {
+        const char *e = getenv("INVGPU_GJ_KERNEL");
+        which = (e && !strcmp(e, "rowlane")) ? 1 : (e && !strcmp(e, "generic")) ? 2 : 0;
+    }
+    if (which == 2) return INVGPU_NO_FAST_PATH;
+    if (which == 0 && n > INVGPU_GJT_MIN_N(T)) { INVGPU_GJT_ALL(INVGPU_GJT_TRY) }
     INVGPU_GJ_ALL(INVGPU_GJ_TRY)
     return INVGPU_NO_FAST_PATH;
 }
@@ -143,6 +159,8 @@ static int fast_padded(PadIO<T> io, int tier_n, i64 batch, int *dInfo, cudaStrea
     if (op == 0 && n == N && dtype_bytes == (int)sizeof(TT) && STAGES_ == 7) return TR * TC <= 32 ? "warp-tile" : "cta-tile";
 #define INVGPU_TILE_NAME_GP(TT, N, TR, TC, MINB) \
     if (op == 2 && n == N && dtype_bytes == (int)sizeof(TT)) return TR * TC <= 32 ? "warp-tile" : "cta-tile";
+#define INVGPU_GJT_NAME(TT, N, TR, TC, MINB) \
+    if (op == 1 && n > INVGPU_GJT_MIN_N(TT) && n <= N && dtype_bytes == (int)sizeof(TT)) return TR * TC <= 32 ? "gj-tile-warp" : "gj-tile-cta";
 #define INVGPU_GJ_NAME(TT, N, ROWS, MINB) \
     if (op == 1 && n <= N && dtype_bytes == (int)sizeof(TT)) return "warp-rowlane";
 #define INVGPU_SWEEP_NAME(V, TT, N, TR, TC, UNROLL, MINB, BLK) \
@@ -152,6 +170,7 @@ static int fast_padded(PadIO<T> io, int tier_n, i64 batch, int *dInfo, cudaStrea
 static const char *fast_tier_name(int op, int n, int dtype_bytes) {
     INVGPU_SWEEP_ALL(INVGPU_SWEEP_NAME)
     INVGPU_SWEEP_GP_ALL(INVGPU_SWEEP_GP_NAME)
+    INVGPU_GJT_ALL(INVGPU_GJT_NAME)
     INVGPU_GJ_ALL(INVGPU_GJ_NAME)
     INVGPU_TILE_SPD_ALL(INVGPU_TILE_NAME)
     INVGPU_TILE_GP_ALL(INVGPU_TILE_NAME_GP)

@@ -104,3 +104,10 @@
     X(float, 96, 8, 8, 4) X(float, 128, 16, 8, 3) X(float, 192, 16, 16, 1) X(float, 256, 16, 16, 1)
 #define INVGPU_SWEEP_PAD_F64(X) X(double, 16, 2, 2, 2) X(double, 32, 4, 4, 2) X(double, 64, 8, 8, 4) X(double, 128, 16, 16, 1)
 #define INVGPU_SWEEP_PAD_ALL(X) INVGPU_SWEEP_PAD_F32(X) INVGPU_SWEEP_PAD_F64(X)
+
+// general inverse, 2-D register tile Gauss-Jordan (gj_tile_kernels.cuh):  X(T, N, TR, TC, MINB); N = padded order, ascending
+// (thread grids measured on B200, fraction of the HBM roofline: n = 64 fp32 8x4: 0.067, 2x16: 0.057; n = 128 fp32 16x8: 0.039,
+//  4x32: 0.047 -- the kernel is instruction-cache bound, a one-block-wide tile has 4 step bodies instead of N / TC)
+#define INVGPU_GJT_F32(X) X(float, 64, 8, 4, 3) X(float, 128, 4, 32, 3)
+#define INVGPU_GJT_F64(X) X(double, 32, 4, 4, 2) X(double, 64, 8, 8, 4) X(double, 128, 16, 16, 1)
+#define INVGPU_GJT_ALL(X) INVGPU_GJT_F32(X) INVGPU_GJT_F64(X)

@@ -16,6 +16,9 @@ int launch_tile_gp(GpIO<T> io, i64 batch, int *dInfo, cudaStream_t st, DeviceSta
 template <typename T, int N, int ROWS, typename IO, int MINB>
 int launch_gj(IO io, int n, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds);
 
+template <typename T, int N, int TR, int TC, typename IO, int MINB>
+int launch_gj_tile(IO io, int n, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds);
+
 template <typename T, int N, int TR, int TC, bool STAGE, int MINB>
 int launch_onesweep(StridedIO<T> io, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds);
 
@@ -44,6 +47,7 @@ int launch_sweep_tma(StridedIO<T> io, i64 batch, int *dInfo, cudaStream_t st, De
 #include "gj_kernels.cuh"
 #include "onesweep_kernels.cuh"
 #include "sweep_kernels.cuh"
+#include "gj_tile_kernels.cuh"
 
 namespace invgpu {
 
@@ -189,6 +193,19 @@ int launch_gj(IO io, int n, i64 batch, int *dInfo, cudaStream_t st, DeviceState 
     return (int)cudaGetLastError();
 }
 
+template <typename T, int N, int TR, int TC, typename IO, int MINB>
+int launch_gj_tile(IO io, int n, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds) {
+    using G = GjtGeo<T, N, TR, TC>;
+    auto kern = gj_tile_kernel<T, N, TR, TC, IO, MINB>;
+    const size_t smem = (size_t)G::MPB * G::WORDS * sizeof(T);
+    int grid = 0;
+    int rc = persistent_grid(kern, G::BLOCK, smem, (batch + G::MPB - 1) / G::MPB, ds, &grid);
+    if (rc) return rc;
+    kern<<<grid, G::BLOCK, smem, st>>>(io, n, batch, dInfo);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return (int)cudaGetLastError();
+}
+
 template <typename T, int N, int TR, int TC, bool PERM, int STAGES, int MINB>
 int launch_tile_spd(StridedIO<T> io, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds) {
     using G = TileGeo<N, TR, TC, PERM>;
@@ -225,6 +242,9 @@ int launch_tile_gp(GpIO<T> io, i64 batch, int *dInfo, cudaStream_t st, DeviceSta
 #define INVGPU_GJ_INSTANTIATE(T, N, ROWS, MINB) \
     template int invgpu::launch_gj<T, N, ROWS, invgpu::StridedIO<T>, MINB>(invgpu::StridedIO<T>, int, invgpu::i64, int *, cudaStream_t, invgpu::DeviceState *); \
     template int invgpu::launch_gj<T, N, ROWS, invgpu::PtrIO<T>, MINB>(invgpu::PtrIO<T>, int, invgpu::i64, int *, cudaStream_t, invgpu::DeviceState *);
+#define INVGPU_GJT_INSTANTIATE(T, N, TR, TC, MINB) \
+    template int invgpu::launch_gj_tile<T, N, TR, TC, invgpu::StridedIO<T>, MINB>(invgpu::StridedIO<T>, int, invgpu::i64, int *, cudaStream_t, invgpu::DeviceState *); \
+    template int invgpu::launch_gj_tile<T, N, TR, TC, invgpu::PtrIO<T>, MINB>(invgpu::PtrIO<T>, int, invgpu::i64, int *, cudaStream_t, invgpu::DeviceState *);
 #define INVGPU_ONESWEEP_INSTANTIATE(T, N, TR, TC, STAGE, MINB) \
     template int invgpu::launch_onesweep<T, N, TR, TC, STAGE, MINB>(invgpu::StridedIO<T>, invgpu::i64, int *, cudaStream_t, invgpu::DeviceState *);
 #define INVGPU_SWEEP_TMA_INSTANTIATE(V, T, N, TR, TC, UNROLL, MINB) \

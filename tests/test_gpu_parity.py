@@ -256,6 +256,29 @@ def test_general_flags_match_oracle(api, dtype):
     assert normwise_err(orc.from_colmajor(got, n)[good], orc.from_colmajor(want, n)[good]) <= TOL[np.dtype(dtype)]
 
 
+@pytest.mark.parametrize("n", [40, 64, 100, 128])
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_general_flags_tile_tiers(api, n, dtype):
+    """Orders above 32 run on the 2-D register-tile Gauss-Jordan kernel (gj_tile_kernels.cuh): flags are
+    sgetrf's (first column without a non-zero pivot), a NaN column counts as singular, outputs of flagged
+    matrices are NaN and the rest of the batch is unaffected."""
+    rng = np.random.default_rng(n)
+    a = rng.random((6, n, n)) + np.eye(n)
+    a[1, :, n // 2] = 0.0            # zero column: pivot n/2 + 1 is exactly zero
+    a[3] = 0.0                       # zero matrix: info 1
+    a[4, :, n - 1] = np.nan          # NaN column: singular at the last step
+    flat = orc.to_colmajor(a.astype(dtype))
+    got, info = api.general_inverse_host(flat, n)
+    want, oinfo = orc.gauss_jordan_inverse(flat, n)
+    np.testing.assert_array_equal(info, oinfo)
+    assert info[1] == n // 2 + 1 and info[3] == 1 and info[4] == n and (info != 0).sum() == 3
+    good = info == 0
+    tol = max(TOL[np.dtype(dtype)], 16 * np.finfo(dtype).eps * 1e3)
+    assert normwise_err(orc.from_colmajor(got, n)[good], orc.from_colmajor(want, n)[good]) <= tol
+    assert np.isnan(orc.from_colmajor(got, n)[~good]).all()
+    assert api.tier_name("general", n, dtype).startswith("gj-tile")
+
+
 # --------------------------------------------------------------------------------------- GP mean / variance
 @pytest.mark.parametrize("n", [8, 16, 32, 64])
 @pytest.mark.parametrize("dtype", DTYPES)

@@ -45,7 +45,25 @@ struct MixedItem {
 // the FMAs of its pivots); loads / stores are bounds-checked scalar accesses (lda = n: no alignment).
 template <typename T>
 struct PadIO {
-    const MixedItem *items;
+    // exactly one addressing mode is set: a work list (mixed dimensions), per-matrix pointer arrays
+    // (the reference's `Array *devAs` flavour, uniform order n) or a strided dense batch (uniform n)
+    const MixedItem *items = nullptr;
+    T *const *in_ptrs = nullptr;
+    T *const *out_ptrs = nullptr;
+    const T *in_base = nullptr;
+    T *out_base = nullptr;
+    i64 in_stride = 0, out_stride = 0;
+    int n = 0;
+    __device__ __forceinline__ void get(i64 k, const T *&src, T *&dst, int &order, i64 &info_index) const {
+        if (items) {
+            const MixedItem it = items[k];
+            src = static_cast<const T *>(it.in); dst = static_cast<T *>(it.out); order = it.n; info_index = it.index;
+        } else if (in_ptrs) {
+            src = in_ptrs[k]; dst = out_ptrs[k]; order = n; info_index = k;
+        } else {
+            src = in_base + k * in_stride; dst = out_base + k * out_stride; order = n; info_index = k;
+        }
+    }
 };
 template <typename IO> struct IoTraits { static constexpr bool PADDED = false; };
 template <typename T> struct IoTraits<PadIO<T>> { static constexpr bool PADDED = true; };

@@ -77,14 +77,47 @@ static int fast_spd_dense(StridedIO<T> io, int n, i64 batch, int *dInfo, cudaStr
     return INVGPU_NO_FAST_PATH;
 }
 
+// smallest padded sweep tier >= n that is instantiated for T (0: none)
+#define INVGPU_SWEEP_PAD_PICK(TT, N, TR, TC, MINB) \
+    if (std::is_same<T, TT>::value && n <= N && (best == 0 || N < best)) best = N;
+template <typename T>
+static int padded_tier_for(int n) {
+    int best = 0;
+    INVGPU_SWEEP_PAD_ALL(INVGPU_SWEEP_PAD_PICK)
+    return best;
+}
+template <typename T>
+static int fast_padded(PadIO<T> io, int tier_n, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds);
+
+// Inverse of a batch the aligned dense kernels cannot take (pointer arrays, odd orders, unaligned strides):
+// the padded sweep tier -- blockdiag(A, I) in the register tile, bounds-checked scalar I/O.
+template <typename T>
+static int fast_spd_padded(PadIO<T> pio, int n, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds) {
+    static int off = -1;                              // INVGPU_SPD_KERNEL=generic keeps such batches on the shared-memory tier
+    if (off < 0) { const char *e = getenv("INVGPU_SPD_KERNEL"); off = (e && !strcmp(e, "generic")) ? 1 : 0; }
+    const int tier = off ? 0 : padded_tier_for<T>(n);
+    if (!tier) return INVGPU_NO_FAST_PATH;
+    pio.n = n;
+    return fast_padded<T>(pio, tier, batch, dInfo, st, ds);
+}
+
 template <typename T, typename IO, int STAGES>
-struct FastSpd {   // pointer-array batches: per-matrix alignment is unknown on the host -> generic tier
-    static int run(IO, int, i64, int *, cudaStream_t, DeviceState *) { return INVGPU_NO_FAST_PATH; }
+struct FastSpd {   // pointer-array batches: inverse on the padded tiers, staged calls on the generic tier
+    static int run(IO io, int n, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds) {
+        if (STAGES != SPD_INVERSE) return INVGPU_NO_FAST_PATH;
+        PadIO<T> pio;
+        pio.in_ptrs = io.in; pio.out_ptrs = io.out;
+        return fast_spd_padded<T>(pio, n, batch, dInfo, st, ds);
+    }
 };
 template <typename T, int STAGES>
 struct FastSpd<T, StridedIO<T>, STAGES> {
     static int run(StridedIO<T> io, int n, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds) {
-        return fast_spd_dense<T, STAGES>(io, n, batch, dInfo, st, ds);
+        const int rc = fast_spd_dense<T, STAGES>(io, n, batch, dInfo, st, ds);
+        if (rc != INVGPU_NO_FAST_PATH || STAGES != SPD_INVERSE) return rc;
+        PadIO<T> pio;
+        pio.in_base = io.in; pio.out_base = io.out; pio.in_stride = io.in_stride; pio.out_stride = io.out_stride;
+        return fast_spd_padded<T>(pio, n, batch, dInfo, st, ds);
     }
 };
 
@@ -174,6 +207,7 @@ static const char *fast_tier_name(int op, int n, int dtype_bytes) {
     INVGPU_GJ_ALL(INVGPU_GJ_NAME)
     INVGPU_TILE_SPD_ALL(INVGPU_TILE_NAME)
     INVGPU_TILE_GP_ALL(INVGPU_TILE_NAME_GP)
+    if (op == 0 && ((dtype_bytes == 4 && padded_tier_for<float>(n)) || (dtype_bytes == 8 && padded_tier_for<double>(n)))) return "sweep-padded";
     return "generic";
 }
 

@@ -606,8 +606,9 @@ sweep_spd_kernel(IO io, i64 batch, int *__restrict__ info) {
         int nn = N;                                                // order of the matrix inside the N x N tile
         i64 iidx = m;                                              // where its info goes
         if constexpr (IoTraits<IO>::PADDED) {
-            const MixedItem it = io.items[valid ? m : batch - 1];
-            src = static_cast<const T *>(it.in); dst = static_cast<T *>(it.out); nn = it.n; iidx = it.index;
+            const T *s0; T *d0;
+            io.get(valid ? m : batch - 1, s0, d0, nn, iidx);
+            src = s0; dst = d0;
         } else {
             src = io.src(valid ? m : batch - 1); dst = io.dst(valid ? m : batch - 1);
         }

@@ -532,11 +532,39 @@ struct Sweep2Ranges {
 };
 
 // the whole elimination of one matrix whose tile is loaded: prologue publish + all steps
+// BLK == 0: the same pivots WITHOUT look-ahead: publish -> barrier -> update, every pivot of a range through one
+// rolled body (half the code of the look-ahead form, whose last pivot of a range is peeled because the slots
+// of ITS successor differ).  An experiment on instruction-cache pressure (variant 8).
+template <typename T, int N, int TR, int TC, int MODE, int S, int W, int SUB>
+struct SweepRangesPlain {
+    static __device__ __forceinline__ void run(Pair2<T> (&ap)[N / TR / 2][N / TC], Pair2<T> (&rhs)[SweepGeo<N, TR, TC>::NC],
+                                               T *sm, int ti, int tj, T &dmin, T &d, T &acc_m, T &acc_q) {
+        using SG = SweepGeo<N, TR, TC>;
+        constexpr int PM = SG::PMIN;
+        constexpr int Q0 = S * SG::PMAX + SUB * PM;
+        constexpr int GR = Q0 / TR, HC = Q0 / TC;
+        constexpr int J0 = ((4 * S + W) * SG::SUBS + SUB) * PM;
+        #pragma unroll 1
+        for (int t = 0; t < PM; ++t) {
+            T *z = sm + ((J0 + t) & 1) * SG::LINE;
+            sweep_publish<T, N, TR, TC, MODE, GR, HC, W>(ap, rhs, z, ti, tj, Q0 + t);
+            tile_sync<SG::LANES>();
+            sweep_step<T, N, TR, TC, MODE, S, W, 0, 0, 0, false>(ap, rhs, z, z, ti, tj, 0, dmin, d, acc_m, acc_q);
+        }
+        constexpr int SUBN = (SUB + 1 < SG::SUBS) ? SUB + 1 : 0;
+        constexpr int WN = (SUBN != 0) ? W : (W == 3 ? 0 : W + 1);
+        constexpr int SN = (SUBN != 0 || W != 3) ? S : S + 1;
+        if constexpr (SN < SG::NS) SweepRangesPlain<T, N, TR, TC, MODE, SN, WN, SUBN>::run(ap, rhs, sm, ti, tj, dmin, d, acc_m, acc_q);
+    }
+};
+
 template <typename T, int N, int TR, int TC, int MODE, bool UNROLL, int BLK>
 __device__ __forceinline__ void sweep_eliminate(Pair2<T> (&ap)[N / TR / 2][N / TC], Pair2<T> (&rhs)[SweepGeo<N, TR, TC>::NC],
                                                 T *sm, int ti, int tj, T &dmin, T &d, T &acc_m, T &acc_q) {
     using SG = SweepGeo<N, TR, TC>;
-    if constexpr (BLK == 2) {
+    if constexpr (BLK == 0) {
+        SweepRangesPlain<T, N, TR, TC, MODE, 0, 0, 0>::run(ap, rhs, sm, ti, tj, dmin, d, acc_m, acc_q);
+    } else if constexpr (BLK == 2) {
         sweep2_publish<T, N, TR, TC, MODE, 0, 0, 0>(ap, rhs, sm, ti, tj, 0);
         tile_sync<SG::LANES>();
         Sweep2Ranges<T, N, TR, TC, MODE, UNROLL, 0, 0, 0>::run(ap, rhs, sm, ti, tj, dmin, d, acc_m, acc_q);

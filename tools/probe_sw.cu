@@ -23,6 +23,9 @@ using namespace invgpu;
 #ifndef PBLK
 #define PBLK 1
 #endif
+#ifndef PBLK
+#define PBLK 1
+#endif
 #ifdef PGP
 template __global__ void invgpu::sweep_gp_kernel<PT, PN, PTR, PTC, PUNROLL, PMINB, PBLK>(GpIO<PT>, i64, int *, PT *);
 #else

@@ -41,9 +41,9 @@ static bool dense_aligned(const StridedIO<T> &io, int n) {
     if (std::is_same<T, TT>::value && n == N && V == variant)                                        \
         return launch_sweep<TT, N, TR, TC, UNROLL, MINB, BLK>(*reinterpret_cast<StridedIO<TT> *>(&io), batch, dInfo, st, ds);
 
-#define INVGPU_SWEEP_TMA_TRY(V, TT, N, TR, TC, UNROLL, MINB)                                         \
+#define INVGPU_SWEEP_TMA_TRY(V, TT, N, TR, TC, UNROLL, MINB, DIRECT_OUT)                             \
     if (std::is_same<T, TT>::value && n == N && V == variant) {                                      \
-        const int rc_tma = launch_sweep_tma<TT, N, TR, TC, UNROLL, MINB>(*reinterpret_cast<StridedIO<TT> *>(&io), batch, dInfo, st, ds); \
+        const int rc_tma = launch_sweep_tma<TT, N, TR, TC, UNROLL, MINB, DIRECT_OUT>(*reinterpret_cast<StridedIO<TT> *>(&io), batch, dInfo, st, ds); \
         if (rc_tma != INVGPU_TMA_UNAVAILABLE) return rc_tma;                                          \
         variant = 0;                                                                                 \
     }

@@ -895,7 +895,10 @@ struct SweepTmaGeo {
     static __device__ __forceinline__ int off(int chunk, int col) { return col * 128 + ((chunk ^ (col & 7)) << 4); }
 };
 
-template <typename T, int N, int TR, int TC, bool UNROLL, int MINB>
+// DIRECT_OUT: results leave through ordinary 16-byte global stores instead of the bulk store; the box is then free as
+// soon as the tile sits in registers, so the bulk load of the NEXT warp tile is issued before the elimination and
+// lands behind it (prefetch for free) -- at the price of the ~140 store wavefronts per matrix on the LSU pipe.
+template <typename T, int N, int TR, int TC, bool UNROLL, int MINB, bool DIRECT_OUT = false>
 __global__ void __launch_bounds__((SweepGeo<N, TR, TC>::BLOCK), MINB)
 sweep_spd_tma_kernel(const __grid_constant__ TmaMaps maps, const T *__restrict__ in, i64 in_stride, T *__restrict__ out, i64 out_stride,
                      i64 batch, int *__restrict__ info) {
@@ -962,6 +965,10 @@ sweep_spd_tma_kernel(const __grid_constant__ TmaMaps maps, const T *__restrict__
                 for (int c = 0; c < SC; ++c) ap[i][c] = PR::make(-a[2 * i][c], -a[2 * i + 1][c]);
         }
         __syncwarp();                                              // everybody has its tile: the box may be overwritten
+        if (DIRECT_OUT && wl == 0 && tile + tstride < ntiles) {    // prefetch the next warp tile under the elimination
+            mbar_expect_tx(bar, TG::BOX_BYTES);
+            tma_load_2d(box, &maps.in, 0, (int)((tile + tstride) * TG::MPW * N), bar);
+        }
 
         T dmin = T(1), d = T(1), acc_m = T(0), acc_q = T(0);
         PR rhs[SG::NC];
@@ -978,6 +985,45 @@ sweep_spd_tma_kernel(const __grid_constant__ TmaMaps maps, const T *__restrict__
             __syncwarp();
         }
         if (valid && lead && info) info[m] = st;
+        if constexpr (DIRECT_OUT) {
+            if (valid) {
+                T *__restrict__ dst = out + m * out_stride;
+                #pragma unroll
+                for (int g = 0; g < SG::NGR; ++g) {
+                    #pragma unroll
+                    for (int h = 0; h < SG::NGC; ++h) {
+                        const int br = TR * g + ti, bc = TC * h + tj;
+                        if (bad) {
+                            #pragma unroll
+                            for (int v = 0; v < 4; ++v)
+                                stg4(dst + (size_t)(4 * bc + v) * N + 4 * br, dev_nan<T>(), dev_nan<T>(), dev_nan<T>(), dev_nan<T>());
+                            continue;
+                        }
+                        if (SG::upper(2 * g, 4 * h)) continue;
+                        T b[4][4];
+                        #pragma unroll
+                        for (int v = 0; v < 4; ++v) {
+                            b[0][v] = ap[2 * g][4 * h + v].lo(); b[1][v] = ap[2 * g][4 * h + v].hi();
+                            b[2][v] = ap[2 * g + 1][4 * h + v].lo(); b[3][v] = ap[2 * g + 1][4 * h + v].hi();
+                        }
+                        if (br == bc) {
+                            #pragma unroll
+                            for (int v = 0; v < 4; ++v)
+                                stg4(dst + (size_t)(4 * bc + v) * N + 4 * br, v <= 0 ? b[0][v] : b[v][0], v <= 1 ? b[1][v] : b[v][1],
+                                     v <= 2 ? b[2][v] : b[v][2], b[3][v]);
+                        } else if (br > bc) {
+                            #pragma unroll
+                            for (int v = 0; v < 4; ++v)
+                                stg4(dst + (size_t)(4 * bc + v) * N + 4 * br, b[0][v], b[1][v], b[2][v], b[3][v]);
+                            #pragma unroll
+                            for (int ww = 0; ww < 4; ++ww)
+                                stg4(dst + (size_t)(4 * br + ww) * N + 4 * bc, b[ww][0], b[ww][1], b[ww][2], b[ww][3]);
+                        }
+                    }
+                }
+            }
+            continue;
+        }
         // ---- result -> swizzled box (both triangles; NaN for a flagged matrix)
         #pragma unroll
         for (int g = 0; g < SG::NGR; ++g) {

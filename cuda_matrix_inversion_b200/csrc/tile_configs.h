@@ -85,8 +85,8 @@
 // wide tiles (TR > TC) win by 3-7 % at n = 64 / 128 (row owners of a pivot sit in one quarter-warp).
 #define INVGPU_SWEEP_ALL(X) INVGPU_SWEEP_F32(X) INVGPU_SWEEP_F64(X)
 
-// the same kernel with TMA tile I/O (sweep_spd_tma_kernel; columns of exactly 128 bytes):  X(V, T, N, TR, TC, UNROLL, MINB)
-#define INVGPU_SWEEP_TMA_F32(X) X(6, float, 32, 2, 4, false, 3) X(7, float, 32, 4, 2, false, 3)
+// the same kernel with TMA tile I/O (sweep_spd_tma_kernel; columns of exactly 128 bytes):  X(V, T, N, TR, TC, UNROLL, MINB, DIRECT_OUT)
+#define INVGPU_SWEEP_TMA_F32(X) X(6, float, 32, 2, 4, false, 3, false) X(7, float, 32, 2, 4, false, 3, true)
 #define INVGPU_SWEEP_TMA_F64(X)
 #define INVGPU_SWEEP_TMA_ALL(X) INVGPU_SWEEP_TMA_F32(X) INVGPU_SWEEP_TMA_F64(X)
 

@@ -584,7 +584,8 @@ print("variant ok", err)
 
 @pytest.mark.parametrize("variant,n", [(6, 32), (7, 32), (4, 32), (4, 64), (4, 128), (1, 32), (3, 64), (3, 128)])
 def test_sweep_kernel_variants(variant, n):
-    """The non-default sweep configurations (TMA tile I/O: 6, 7; 2x2 block pivots: 4; other thread grids) are selected
+    """The non-default sweep configurations (TMA tile I/O: 6, and 7 = TMA load with prefetch + direct stores; 2x2 block
+    pivots: 4; other thread grids) are selected
     per process with INVGPU_SWEEP_VARIANT, so each runs in a child process: oracle parity, flags, ragged tail."""
     import subprocess
     import sys

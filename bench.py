@@ -44,9 +44,9 @@ METRIC = "batched SPD inversions/sec (32x32 fp32)"
 UNIT = "inversions/s"
 WORKLOAD = "synthetic batched SPD Cholesky inverse, 2^20 x 32x32 fp32 per GPU (BASELINE configs[2])"
 # dram__bytes_read.sum + dram__bytes_write.sum of the headline kernel from the committed `ncu --set full` capture
-# (2^18 matrices per launch there: 1.073962 GB read + 1.029978 GB written), scaled to the 2^20 of one bench launch
-NCU_DRAM_BYTES_PER_LAUNCH = int((1.073962e9 + 1.029978e9) * 4)
-NCU_TRAFFIC_SOURCE = "profiles/r1_sweep32_summary.md (ncu --set full, 2^18 matrices) x 4"
+# (2^18 matrices per launch there: 1.075257 GB read + 1.026820 GB written), scaled to the 2^20 of one bench launch
+NCU_DRAM_BYTES_PER_LAUNCH = int((1.075257e9 + 1.026820e9) * 4)
+NCU_TRAFFIC_SOURCE = "profiles/r1_sweep32_tma_interleaved_summary.md (ncu --set full, 2^18 matrices) x 4"
 
 
 def _peaks():
@@ -353,7 +353,7 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "n": N, "batch_per_gpu": BATCH, "algorithm": "Cholesky-route inverse (potrf+trtri+lauum merged into one symmetric sweep, sweep_kernels.cuh)",
+            "config": {"workload": WORKLOAD, "n": N, "batch_per_gpu": BATCH, "algorithm": "Cholesky-route inverse (potrf+trtri+lauum merged into one symmetric sweep; TMA tile I/O, sweep_kernels.cuh)",
                        "l2_policy": "inputs+outputs 8.6 GB per step >> 126 MB L2", "sharding": f"dp{world}",
                        "kernel_tier": api.tier_name("spd", N)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",

@@ -41,9 +41,9 @@ static bool dense_aligned(const StridedIO<T> &io, int n) {
     if (std::is_same<T, TT>::value && n == N && V == variant)                                        \
         return launch_sweep<TT, N, TR, TC, UNROLL, MINB, BLK>(*reinterpret_cast<StridedIO<TT> *>(&io), batch, dInfo, st, ds);
 
-#define INVGPU_SWEEP_TMA_TRY(V, TT, N, TR, TC, UNROLL, MINB, DIRECT_OUT)                             \
+#define INVGPU_SWEEP_TMA_TRY(V, TT, N, TR, TC, UNROLL, MINB, DIRECT_OUT, INTERLEAVE)                 \
     if (std::is_same<T, TT>::value && n == N && V == variant) {                                      \
-        const int rc_tma = launch_sweep_tma<TT, N, TR, TC, UNROLL, MINB, DIRECT_OUT>(*reinterpret_cast<StridedIO<TT> *>(&io), batch, dInfo, st, ds); \
+        const int rc_tma = launch_sweep_tma<TT, N, TR, TC, UNROLL, MINB, DIRECT_OUT, INTERLEAVE>(*reinterpret_cast<StridedIO<TT> *>(&io), batch, dInfo, st, ds); \
         if (rc_tma != INVGPU_TMA_UNAVAILABLE) return rc_tma;                                          \
         variant = 0;                                                                                 \
     }
@@ -67,7 +67,8 @@ static int fast_spd_dense(StridedIO<T> io, int n, i64 batch, int *dInfo, cudaStr
         int variant = env_variant;
         if (old < 0) { const char *e = getenv("INVGPU_SPD_KERNEL"); old = (e && !strcmp(e, "onesweep")) ? 1 : 0; }
         if (!old && n >= INVGPU_SWEEP_MIN_N) {
-            INVGPU_SWEEP_TMA_ALL(INVGPU_SWEEP_TMA_TRY)             // falls through when the batch is not TMA-describable
+            if (variant == 9) variant = 0;                         // 9 = the default grids without TMA tile I/O
+            else { INVGPU_SWEEP_TMA_ALL(INVGPU_SWEEP_TMA_TRY) }    // falls through when the batch is not TMA-describable
             INVGPU_SWEEP_ALL(INVGPU_SWEEP_TRY)
         }
         INVGPU_ONESWEEP_ALL(INVGPU_ONESWEEP_TRY)

@@ -876,9 +876,11 @@ __device__ __forceinline__ void tma_store_commit_and_wait_read() {
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
-struct TmaMaps {                                                   // two 128-byte CUtensorMap objects, opaque here
-    alignas(64) unsigned char in[128];
+struct TmaMaps {                                                   // 128-byte CUtensorMap objects, opaque here
+    alignas(64) unsigned char in[128];                             // box = the MPW matrices of a warp tile
     alignas(64) unsigned char out[128];
+    alignas(64) unsigned char in1[128];                            // box = one matrix (interleaved-lane variant)
+    alignas(64) unsigned char out1[128];
 };
 
 template <typename T, int N, int TR, int TC>
@@ -890,15 +892,30 @@ struct SweepTmaGeo {
     static constexpr int WARPS = SG::BLOCK / 32;
     static constexpr int MAT_BYTES = N * N * (int)sizeof(T);
     static constexpr int BOX_BYTES = MPW * MAT_BYTES;
+    // INTERLEAVE: every matrix of the warp gets its own box, 128 bytes further than a plain 4 KB stride, so that the
+    // swizzle phase (address bits 7-9) differs from matrix to matrix
+    template <bool INTERLEAVE> __host__ __device__ static constexpr int mstride() { return MAT_BYTES + (INTERLEAVE ? 128 : 0); }
+    template <bool INTERLEAVE> __host__ __device__ static constexpr size_t smem() {
+        return (size_t)WARPS * (INTERLEAVE ? (MPW * mstride<INTERLEAVE>() + 1023) / 1024 * 1024 : MPW * mstride<INTERLEAVE>()) +
+               (size_t)SG::MPB * SG::WORDS * sizeof(T) + WARPS * 8;
+    }
     static constexpr size_t SMEM = (size_t)WARPS * BOX_BYTES + (size_t)SG::MPB * SG::WORDS * sizeof(T) + WARPS * 8;
-    // byte offset of the 16-byte chunk `chunk` of column `col` inside a (1024-byte aligned) swizzled matrix buffer
-    static __device__ __forceinline__ int off(int chunk, int col) { return col * 128 + ((chunk ^ (col & 7)) << 4); }
+    // byte offset of the 16-byte chunk `chunk` of column `col` inside the swizzled buffer of matrix j of the warp
+    // (the warp's first buffer is 1024-byte aligned; j shifts the swizzle phase only in the interleaved layout)
+    template <bool INTERLEAVE>
+    static __device__ __forceinline__ int off(int chunk, int col, int j) {
+        return col * 128 + ((chunk ^ ((col + (INTERLEAVE ? j : 0)) & 7)) << 4);
+    }
 };
 
 // DIRECT_OUT: results leave through ordinary 16-byte global stores instead of the bulk store; the box is then free as
 // soon as the tile sits in registers, so the bulk load of the NEXT warp tile is issued before the elimination and
 // lands behind it (prefetch for free) -- at the price of the ~140 store wavefronts per matrix on the LSU pipe.
-template <typename T, int N, int TR, int TC, bool UNROLL, int MINB, bool DIRECT_OUT = false>
+// INTERLEAVE: lane = ti + TR (mat + MPW tj): the owners of a pivot column of all the matrices of the warp sit in one
+// quarter-warp, so publishing a column costs one shared-memory wavefront per 16-byte store instead of four.  With
+// direct global access that lane map loses the 32-byte runs of the loads / stores (measured -15 %); here the TMA
+// unit does the global side, and per-matrix boxes 128 bytes apart keep the tile accesses conflict-free.
+template <typename T, int N, int TR, int TC, bool UNROLL, int MINB, bool DIRECT_OUT = false, bool INTERLEAVE = false>
 __global__ void __launch_bounds__((SweepGeo<N, TR, TC>::BLOCK), MINB)
 sweep_spd_tma_kernel(const __grid_constant__ TmaMaps maps, const T *__restrict__ in, i64 in_stride, T *__restrict__ out, i64 out_stride,
                      i64 batch, int *__restrict__ info) {
@@ -911,12 +928,15 @@ sweep_spd_tma_kernel(const __grid_constant__ TmaMaps maps, const T *__restrict__
     extern __shared__ __align__(1024) unsigned char smem_raw_tma[];   // 128-byte swizzle repeats every 1024 bytes
     unsigned char *base = smem_raw_tma;
     const int warp = threadIdx.x >> 5, wl = threadIdx.x & 31;
-    const int mat = wl / SG::LANES, lane = wl % SG::LANES;
-    const int ti = lane / TC, tj = lane % TC;
+    int mat, ti, tj;
+    if (INTERLEAVE) { ti = wl % TR; mat = (wl / TR) % TG::MPW; tj = wl / (TR * TG::MPW); }
+    else { mat = wl / SG::LANES; ti = (wl % SG::LANES) / TC; tj = wl % TC; }
     const bool lead = (ti == 0 && tj == 0);
-    unsigned char *box = base + (size_t)warp * TG::BOX_BYTES;      // this warp's MPW matrices
-    unsigned char *buf = box + (size_t)mat * TG::MAT_BYTES;        // this thread's matrix
-    T *lines = reinterpret_cast<T *>(base + (size_t)TG::WARPS * TG::BOX_BYTES);
+    constexpr int MS = TG::template mstride<INTERLEAVE>();
+    constexpr int WBOX = (TG::MPW * MS + (INTERLEAVE ? 1023 : 0)) / (INTERLEAVE ? 1024 : 1) * (INTERLEAVE ? 1024 : 1);   // per-warp bytes, 1 KB multiple
+    unsigned char *box = base + (size_t)warp * WBOX;               // this warp's MPW matrices
+    unsigned char *buf = box + (size_t)mat * MS;                   // this thread's matrix
+    T *lines = reinterpret_cast<T *>(base + (size_t)TG::WARPS * WBOX);
     T *sm = lines + (size_t)(warp * TG::MPW + mat) * SG::WORDS;
     unsigned long long *bar = reinterpret_cast<unsigned long long *>(lines + (size_t)SG::MPB * SG::WORDS) + warp;
 
@@ -931,10 +951,16 @@ sweep_spd_tma_kernel(const __grid_constant__ TmaMaps maps, const T *__restrict__
     const i64 tstride = (i64)gridDim.x * TG::WARPS;
     i64 tile = (i64)blockIdx.x * TG::WARPS + warp;
     unsigned phase = 0;
-    if (tile < ntiles && wl == 0) {
+    auto issue_load = [&](i64 t) {                                 // lane 0 only
         mbar_expect_tx(bar, TG::BOX_BYTES);
-        tma_load_2d(box, &maps.in, 0, (int)(tile * TG::MPW * N), bar);
-    }
+        if (INTERLEAVE) {
+            #pragma unroll
+            for (int j = 0; j < TG::MPW; ++j) tma_load_2d(box + j * MS, &maps.in1, 0, (int)((t * TG::MPW + j) * N), bar);
+        } else {
+            tma_load_2d(box, &maps.in, 0, (int)(t * TG::MPW * N), bar);
+        }
+    };
+    if (tile < ntiles && wl == 0) issue_load(tile);
     #pragma unroll 1
     for (; tile < ntiles; tile += tstride) {
         const i64 m = tile * TG::MPW + mat;
@@ -954,7 +980,7 @@ sweep_spd_tma_kernel(const __grid_constant__ TmaMaps maps, const T *__restrict__
                     for (int p = 0; p < 4; ++p) {
                         // lower block (br >= bc): its transposed twin from the UPPER triangle: column 4 br + p, rows 4 bc ..
                         if (!SG::upper(2 * g, 4 * h) && br >= bc)
-                            ld4(reinterpret_cast<const T *>(buf + TG::off(bc, 4 * br + p)), a[4 * g + p][4 * h], a[4 * g + p][4 * h + 1],
+                            ld4(reinterpret_cast<const T *>(buf + TG::template off<INTERLEAVE>(bc, 4 * br + p, mat)), a[4 * g + p][4 * h], a[4 * g + p][4 * h + 1],
                                 a[4 * g + p][4 * h + 2], a[4 * g + p][4 * h + 3]);
                         else { a[4 * g + p][4 * h] = T(0); a[4 * g + p][4 * h + 1] = T(0); a[4 * g + p][4 * h + 2] = T(0); a[4 * g + p][4 * h + 3] = T(0); }
                     }
@@ -965,10 +991,7 @@ sweep_spd_tma_kernel(const __grid_constant__ TmaMaps maps, const T *__restrict__
                 for (int c = 0; c < SC; ++c) ap[i][c] = PR::make(-a[2 * i][c], -a[2 * i + 1][c]);
         }
         __syncwarp();                                              // everybody has its tile: the box may be overwritten
-        if (DIRECT_OUT && wl == 0 && tile + tstride < ntiles) {    // prefetch the next warp tile under the elimination
-            mbar_expect_tx(bar, TG::BOX_BYTES);
-            tma_load_2d(box, &maps.in, 0, (int)((tile + tstride) * TG::MPW * N), bar);
-        }
+        if (DIRECT_OUT && wl == 0 && tile + tstride < ntiles) issue_load(tile + tstride);   // prefetch under the elimination
 
         T dmin = T(1), d = T(1), acc_m = T(0), acc_q = T(0);
         PR rhs[SG::NC];
@@ -1033,7 +1056,7 @@ sweep_spd_tma_kernel(const __grid_constant__ TmaMaps maps, const T *__restrict__
                 if (bad) {
                     #pragma unroll
                     for (int v = 0; v < 4; ++v)
-                        st4(reinterpret_cast<T *>(buf + TG::off(br, 4 * bc + v)), dev_nan<T>(), dev_nan<T>(), dev_nan<T>(), dev_nan<T>());
+                        st4(reinterpret_cast<T *>(buf + TG::template off<INTERLEAVE>(br, 4 * bc + v, mat)), dev_nan<T>(), dev_nan<T>(), dev_nan<T>(), dev_nan<T>());
                     continue;
                 }
                 if (SG::upper(2 * g, 4 * h)) continue;
@@ -1046,27 +1069,29 @@ sweep_spd_tma_kernel(const __grid_constant__ TmaMaps maps, const T *__restrict__
                 if (br == bc) {
                     #pragma unroll
                     for (int v = 0; v < 4; ++v)
-                        st4(reinterpret_cast<T *>(buf + TG::off(br, 4 * bc + v)), v <= 0 ? b[0][v] : b[v][0], v <= 1 ? b[1][v] : b[v][1],
+                        st4(reinterpret_cast<T *>(buf + TG::template off<INTERLEAVE>(br, 4 * bc + v, mat)), v <= 0 ? b[0][v] : b[v][0], v <= 1 ? b[1][v] : b[v][1],
                             v <= 2 ? b[2][v] : b[v][2], b[3][v]);
                 } else if (br > bc) {
                     #pragma unroll
                     for (int v = 0; v < 4; ++v)
-                        st4(reinterpret_cast<T *>(buf + TG::off(br, 4 * bc + v)), b[0][v], b[1][v], b[2][v], b[3][v]);
+                        st4(reinterpret_cast<T *>(buf + TG::template off<INTERLEAVE>(br, 4 * bc + v, mat)), b[0][v], b[1][v], b[2][v], b[3][v]);
                     #pragma unroll
                     for (int ww = 0; ww < 4; ++ww)
-                        st4(reinterpret_cast<T *>(buf + TG::off(bc, 4 * br + ww)), b[ww][0], b[ww][1], b[ww][2], b[ww][3]);
+                        st4(reinterpret_cast<T *>(buf + TG::template off<INTERLEAVE>(bc, 4 * br + ww, mat)), b[ww][0], b[ww][1], b[ww][2], b[ww][3]);
                 }
             }
         }
         fence_proxy_async();                                       // generic-proxy writes -> visible to the TMA unit
         __syncwarp();
         if (wl == 0) {
-            tma_store_2d(&maps.out, 0, (int)(tile * TG::MPW * N), box);
-            tma_store_commit_and_wait_read();                      // the box has been read: it can take the next tile
-            if (tile + tstride < ntiles) {
-                mbar_expect_tx(bar, TG::BOX_BYTES);
-                tma_load_2d(box, &maps.in, 0, (int)((tile + tstride) * TG::MPW * N), bar);
+            if (INTERLEAVE) {
+                #pragma unroll
+                for (int j = 0; j < TG::MPW; ++j) tma_store_2d(&maps.out1, 0, (int)((tile * TG::MPW + j) * N), box + j * MS);
+            } else {
+                tma_store_2d(&maps.out, 0, (int)(tile * TG::MPW * N), box);
             }
+            tma_store_commit_and_wait_read();                      // the box has been read: it can take the next tile
+            if (tile + tstride < ntiles) issue_load(tile + tstride);
         }
         __syncwarp();
     }

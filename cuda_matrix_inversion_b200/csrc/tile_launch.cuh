@@ -33,7 +33,7 @@ int launch_sweep_pad(PadIO<T> io, i64 batch, int *dInfo, cudaStream_t st, Device
 
 // returns INVGPU_TMA_UNAVAILABLE when the batch cannot be described to the TMA unit (strides, size, driver)
 #define INVGPU_TMA_UNAVAILABLE (-1001)
-template <typename T, int N, int TR, int TC, bool UNROLL, int MINB, bool DIRECT_OUT>
+template <typename T, int N, int TR, int TC, bool UNROLL, int MINB, bool DIRECT_OUT, bool INTERLEAVE>
 int launch_sweep_tma(StridedIO<T> io, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds);
 
 }  // namespace invgpu
@@ -113,7 +113,7 @@ static int make_batch_tensor_map(void *out128, const T *base, i64 batch, int mat
     return 0;
 }
 
-template <typename T, int N, int TR, int TC, bool UNROLL, int MINB, bool DIRECT_OUT>
+template <typename T, int N, int TR, int TC, bool UNROLL, int MINB, bool DIRECT_OUT, bool INTERLEAVE>
 int launch_sweep_tma(StridedIO<T> io, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds) {
     using SG = SweepGeo<N, TR, TC>;
     using TG = SweepTmaGeo<T, N, TR, TC>;
@@ -124,14 +124,19 @@ int launch_sweep_tma(StridedIO<T> io, i64 batch, int *dInfo, cudaStream_t st, De
     if (rc) return rc;
     rc = make_batch_tensor_map<T, N>(maps.out, io.out, batch, TG::MPW);
     if (rc) return rc;
-    auto kern = sweep_spd_tma_kernel<T, N, TR, TC, UNROLL, MINB, DIRECT_OUT>;
+    rc = make_batch_tensor_map<T, N>(maps.in1, io.in, batch, 1);
+    if (rc) return rc;
+    rc = make_batch_tensor_map<T, N>(maps.out1, io.out, batch, 1);
+    if (rc) return rc;
+    auto kern = sweep_spd_tma_kernel<T, N, TR, TC, UNROLL, MINB, DIRECT_OUT, INTERLEAVE>;
+    constexpr size_t SMEM = TG::template smem<INTERLEAVE>();
     int grid = 0;
-    rc = persistent_grid(kern, SG::BLOCK, TG::SMEM, (batch + SG::MPB - 1) / SG::MPB, ds, &grid);
+    rc = persistent_grid(kern, SG::BLOCK, SMEM, (batch + SG::MPB - 1) / SG::MPB, ds, &grid);
     if (rc) return rc;
     static int trace = -1;
     if (trace < 0) { const char *e = getenv("INVGPU_TRACE"); trace = (e && atoi(e) > 0) ? 1 : 0; }
-    if (trace) fprintf(stderr, "[invgpu] sweep_spd_tma_kernel<n=%d, %dx%d, direct_out=%d> grid %d smem %zu\n", N, TR, TC, (int)DIRECT_OUT, grid, (size_t)TG::SMEM);
-    kern<<<grid, SG::BLOCK, TG::SMEM, st>>>(maps, io.in, io.in_stride, io.out, io.out_stride, batch, dInfo);
+    if (trace) fprintf(stderr, "[invgpu] sweep_spd_tma_kernel<n=%d, %dx%d, direct_out=%d, interleave=%d> grid %d smem %zu\n", N, TR, TC, (int)DIRECT_OUT, (int)INTERLEAVE, grid, SMEM);
+    kern<<<grid, SG::BLOCK, SMEM, st>>>(maps, io.in, io.in_stride, io.out, io.out_stride, batch, dInfo);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return (int)cudaGetLastError();
 }
@@ -247,8 +252,8 @@ int launch_tile_gp(GpIO<T> io, i64 batch, int *dInfo, cudaStream_t st, DeviceSta
     template int invgpu::launch_gj_tile<T, N, TR, TC, invgpu::PtrIO<T>, MINB>(invgpu::PtrIO<T>, int, invgpu::i64, int *, cudaStream_t, invgpu::DeviceState *);
 #define INVGPU_ONESWEEP_INSTANTIATE(T, N, TR, TC, STAGE, MINB) \
     template int invgpu::launch_onesweep<T, N, TR, TC, STAGE, MINB>(invgpu::StridedIO<T>, invgpu::i64, int *, cudaStream_t, invgpu::DeviceState *);
-#define INVGPU_SWEEP_TMA_INSTANTIATE(V, T, N, TR, TC, UNROLL, MINB, DIRECT_OUT) \
-    template int invgpu::launch_sweep_tma<T, N, TR, TC, UNROLL, MINB, DIRECT_OUT>(invgpu::StridedIO<T>, invgpu::i64, int *, cudaStream_t, invgpu::DeviceState *);
+#define INVGPU_SWEEP_TMA_INSTANTIATE(V, T, N, TR, TC, UNROLL, MINB, DIRECT_OUT, INTERLEAVE) \
+    template int invgpu::launch_sweep_tma<T, N, TR, TC, UNROLL, MINB, DIRECT_OUT, INTERLEAVE>(invgpu::StridedIO<T>, invgpu::i64, int *, cudaStream_t, invgpu::DeviceState *);
 #define INVGPU_SWEEP_PAD_INSTANTIATE(T, N, TR, TC, MINB) \
     template int invgpu::launch_sweep_pad<T, N, TR, TC, MINB>(invgpu::PadIO<T>, invgpu::i64, int *, cudaStream_t, invgpu::DeviceState *);
 #define INVGPU_SWEEP_GP_INSTANTIATE(V, T, N, TR, TC, UNROLL, MINB, BLK) \

@@ -582,10 +582,10 @@ print("variant ok", err)
 """
 
 
-@pytest.mark.parametrize("variant,n", [(6, 32), (7, 32), (4, 32), (4, 64), (4, 128), (1, 32), (3, 64), (3, 128)])
+@pytest.mark.parametrize("variant,n", [(0, 32), (6, 32), (7, 32), (9, 32), (4, 32), (4, 64), (4, 128), (1, 32), (3, 64), (3, 128)])
 def test_sweep_kernel_variants(variant, n):
-    """The non-default sweep configurations (TMA tile I/O: 6, and 7 = TMA load with prefetch + direct stores; 2x2 block
-    pivots: 4; other thread grids) are selected
+    """The non-default sweep configurations (n = 32: 0 = default = TMA tile I/O with interleaved lanes, 6 = TMA without
+    interleaving, 7 = TMA load with prefetch + direct stores, 9 = direct global access; 2x2 block pivots: 4; other grids) are selected
     per process with INVGPU_SWEEP_VARIANT, so each runs in a child process: oracle parity, flags, ragged tail."""
     import subprocess
     import sys
@@ -596,5 +596,7 @@ def test_sweep_kernel_variants(variant, n):
                        capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stdout + p.stderr
     assert "variant ok" in p.stdout
-    if variant in (6, 7):
+    if n == 32 and variant in (0, 6, 7):
         assert "sweep_spd_tma_kernel" in p.stderr      # the TMA kernel really ran (no silent fallback)
+    if variant == 9:
+        assert "sweep_spd_tma_kernel" not in p.stderr  # the direct-access kernel

@@ -8,6 +8,11 @@
 #include "fast_tiers.cuh"
 #include "mixed_kernels.cuh"
 #include <chrono>
+#include <atomic>
+#include <vector>
+#include <functional>
+#include <array>
+#include <thread>
 #include <algorithm>
 
 #include "../../include/invgpu.h"
@@ -342,15 +347,33 @@ static int run_mixed_spd(T *const *hIn, T *const *hOut, const int *hN, i64 count
     static int timing = -1;
     if (timing < 0) { const char *e = getenv("INVGPU_MIXED_TIMING"); timing = (e && atoi(e) > 0) ? 1 : 0; }
     const auto t_plan0 = std::chrono::steady_clock::now();
-    // counting sort by n, descending inside each bucket (longest work first): two passes, no comparisons
+    // counting sort by n, descending inside each tier: two passes over the batch, no comparisons; both passes are
+    // split over a few host threads (per-thread histograms give every thread its own output ranges)
+    const int nthr = (count >= (1 << 16)) ? (int)std::min<unsigned>(8, std::max(1u, std::thread::hardware_concurrency())) : 1;
+    std::vector<std::array<i64, 257>> thist(nthr);
+    std::atomic<int> bad_arg{0};
+    auto slice = [&](int t, i64 &b, i64 &e) { b = count * t / nthr; e = count * (t + 1) / nthr; };
+    auto run_threads = [&](const std::function<void(int)> &fn) {
+        if (nthr == 1) { fn(0); return; }
+        std::vector<std::thread> pool;
+        for (int t = 1; t < nthr; ++t) pool.emplace_back(fn, t);
+        fn(0);
+        for (auto &th : pool) th.join();
+    };
+    run_threads([&](int t) {
+        i64 b, e; slice(t, b, e);
+        auto &h = thist[t];
+        h.fill(0);
+        for (i64 i = b; i < e; ++i) {
+            const int n = hN[i];
+            if (n < 1) { bad_arg = INVGPU_EARG; return; }
+            if (n > 256) { bad_arg = INVGPU_EUNSUPPORTED; return; }
+            ++h[n];
+        }
+    });
+    if (bad_arg.load()) return bad_arg.load();
     i64 hist[257];
-    memset(hist, 0, sizeof(hist));
-    for (i64 i = 0; i < count; ++i) {
-        const int n = hN[i];
-        if (n < 1) return INVGPU_EARG;
-        if (n > 256) return INVGPU_EUNSUPPORTED;
-        ++hist[n];
-    }
+    for (int n = 0; n <= 256; ++n) { hist[n] = 0; for (int t = 0; t < nthr; ++t) hist[n] += thist[t][n]; }
     // tier b holds n in (lo_b, hi_b]; position of the first item of order n in the concatenated list
     constexpr int NT = DeviceState::kMixedTiers;
     static const int hi[NT] = {16, 24, 32, 48, 64, 96, 128, 192, 256}, lo[NT] = {0, 16, 24, 32, 48, 64, 96, 128, 192};
@@ -383,10 +406,16 @@ static int run_mixed_spd(T *const *hIn, T *const *hOut, const int *hN, i64 count
     char *h = (char *)ds->h_mixed;
     memset(h, 0, HDR);
     MixedItem *items = (MixedItem *)(h + HDR);
-    for (i64 i = 0; i < count; ++i) {                         // scatter straight into the pinned staging buffer
-        MixedItem &it = items[first[hN[i]]++];
-        it.in = hIn[i]; it.out = hOut[i]; it.n = hN[i]; it.index = (int)i;
-    }
+    // thread t writes the items of order n at first[n] + (items of order n owned by threads < t)
+    for (int n = 0; n <= 256; ++n) { i64 run = first[n]; for (int t = 0; t < nthr; ++t) { const i64 c = thist[t][n]; thist[t][n] = run; run += c; } }
+    run_threads([&](int t) {                                  // scatter straight into the pinned staging buffer
+        i64 b, e; slice(t, b, e);
+        auto &pos = thist[t];
+        for (i64 i = b; i < e; ++i) {
+            MixedItem &it = items[pos[hN[i]]++];
+            it.in = hIn[i]; it.out = hOut[i]; it.n = hN[i]; it.index = (int)i;
+        }
+    });
     size_t start[NT];
     size_t off = HDR;
     for (int b = 0; b < NT; ++b) { start[b] = off; off += (size_t)bcount[b] * sizeof(MixedItem); }

@@ -464,6 +464,43 @@ def test_mixed_dimension_scheduler(api, torch, dtype):
         assert np.abs(got - want).max() <= tol * np.abs(want).max(), (i, n)
 
 
+def test_mixed_dimension_scheduler_threaded_planning(api, torch):
+    """Batches of >= 2^16 matrices are planned by several host threads (per-thread histograms + scatter):
+    every matrix must still land in the right tier and report into its own info slot."""
+    rng = np.random.default_rng(99)
+    cnt = 70_000
+    ns = rng.integers(1, 41, cnt).astype(np.int32)              # tiers 16 / 24 / 32 / 48
+    offs = np.concatenate([[0], np.cumsum(ns.astype(np.int64) ** 2)])
+    flat = np.zeros(int(offs[-1]), dtype=np.float32)
+    diag_val = rng.uniform(1.0, 3.0, cnt).astype(np.float32)    # A_i = d_i * I  ->  inverse (1 / d_i) * I
+    for i in np.nonzero(ns <= 40)[0]:
+        n = int(ns[i])
+        flat[offs[i]:offs[i + 1]:n + 1] = diag_val[i]
+    bad = [5, 33_333, 69_999]
+    for b in bad:
+        flat[offs[b]] = -1.0                                     # first pivot negative: info 1
+    d_in = torch.from_numpy(flat).cuda()
+    d_out = torch.zeros_like(d_in)
+    d_info = torch.full((cnt,), -1, dtype=torch.int32, device="cuda")
+    pin = (d_in.data_ptr() + offs[:-1] * 4).astype(np.uint64)
+    pout = (d_out.data_ptr() + offs[:-1] * 4).astype(np.uint64)
+    api.mixed_spd_inverse_device(pin, pout, ns, np.float32, d_info.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    info = d_info.cpu().numpy()
+    out = d_out.cpu().numpy()
+    want_info = np.zeros(cnt, dtype=np.int32)
+    want_info[bad] = 1
+    np.testing.assert_array_equal(info, want_info)
+    good = np.ones(cnt, dtype=bool)
+    good[bad] = False
+    d0 = out[offs[:-1]]                                          # element (0, 0) of every result
+    np.testing.assert_allclose(d0[good], 1.0 / diag_val[good], rtol=1e-5)
+    for i in (0, 1, 12_345, 69_998):                             # whole matrices of a few
+        n = int(ns[i])
+        np.testing.assert_allclose(out[offs[i]:offs[i + 1]].reshape(n, n), np.eye(n) / diag_val[i], rtol=1e-5, atol=1e-7)
+    assert np.isnan(out[offs[5]:offs[6]]).all()
+
+
 # --------------------------------------------------------------------------------------- host pipeline
 def test_host_pipeline_chunking_and_pinned_path(api, torch, monkeypatch):
     """Many chunks, ragged last chunk, pageable and pinned user buffers give identical results."""

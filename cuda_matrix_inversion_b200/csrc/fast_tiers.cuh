@@ -66,6 +66,14 @@ static int fast_spd_dense(StridedIO<T> io, int n, i64 batch, int *dInfo, cudaStr
         if (env_variant < 0) { const char *e = getenv("INVGPU_SWEEP_VARIANT"); env_variant = e ? atoi(e) : 0; }
         int variant = env_variant;
         if (old < 0) { const char *e = getenv("INVGPU_SPD_KERNEL"); old = (e && !strcmp(e, "onesweep")) ? 1 : 0; }
+        if (!old && n == 8 && variant != 9) {                      // one thread per matrix + TMA tile I/O
+#define INVGPU_SPD8_TRY(TT, NBUF, MINB)                                                              \
+            if (std::is_same<T, TT>::value) {                                                         \
+                const int rc8 = launch_spd8_tma<TT, NBUF, MINB>(*reinterpret_cast<StridedIO<TT> *>(&io), batch, dInfo, st, ds); \
+                if (rc8 != INVGPU_TMA_UNAVAILABLE) return rc8;                                         \
+            }
+            INVGPU_SPD8_TMA_ALL(INVGPU_SPD8_TRY)
+        }
         if (!old && n >= INVGPU_SWEEP_MIN_N) {
             if (variant == 9) variant = 0;                         // 9 = the default grids without TMA tile I/O
             else { INVGPU_SWEEP_TMA_ALL(INVGPU_SWEEP_TMA_TRY) }    // falls through when the batch is not TMA-describable
@@ -197,11 +205,14 @@ static int fast_padded(PadIO<T> io, int tier_n, i64 batch, int *dInfo, cudaStrea
     if (op == 1 && n > INVGPU_GJT_MIN_N(TT) && n <= N && dtype_bytes == (int)sizeof(TT)) return TR * TC <= 32 ? "gj-tile-warp" : "gj-tile-cta";
 #define INVGPU_GJ_NAME(TT, N, ROWS, MINB) \
     if (op == 1 && n <= N && dtype_bytes == (int)sizeof(TT)) return "warp-rowlane";
+#define INVGPU_SPD8_NAME(TT, NBUF, MINB) \
+    if (op == 0 && n == 8 && dtype_bytes == (int)sizeof(TT)) return "thread-tma";
 #define INVGPU_SWEEP_NAME(V, TT, N, TR, TC, UNROLL, MINB, BLK) \
     if (op == 0 && V == 0 && n == N && n >= INVGPU_SWEEP_MIN_N && dtype_bytes == (int)sizeof(TT)) return TR * TC <= 32 ? "sweep-warp" : "sweep-cta";
 #define INVGPU_SWEEP_GP_NAME(V, TT, N, TR, TC, UNROLL, MINB, BLK) \
     if (op == 2 && V == 0 && n == N && dtype_bytes == (int)sizeof(TT)) return TR * TC <= 32 ? "sweep-warp" : "sweep-cta";
 static const char *fast_tier_name(int op, int n, int dtype_bytes) {
+    INVGPU_SPD8_TMA_ALL(INVGPU_SPD8_NAME)
     INVGPU_SWEEP_ALL(INVGPU_SWEEP_NAME)
     INVGPU_SWEEP_GP_ALL(INVGPU_SWEEP_GP_NAME)
     INVGPU_GJT_ALL(INVGPU_GJT_NAME)

@@ -894,7 +894,10 @@ struct SweepTmaGeo {
     static constexpr int BOX_BYTES = MPW * MAT_BYTES;
     // INTERLEAVE: every matrix of the warp gets its own box, 128 bytes further than a plain 4 KB stride, so that the
     // swizzle phase (address bits 7-9) differs from matrix to matrix
-    template <bool INTERLEAVE> __host__ __device__ static constexpr int mstride() { return MAT_BYTES + (INTERLEAVE ? 128 : 0); }
+#ifndef INVGPU_TMA_STAGGER
+#define INVGPU_TMA_STAGGER 1       // swizzle lines between the boxes of neighbouring matrices (interleaved layout)
+#endif
+    template <bool INTERLEAVE> __host__ __device__ static constexpr int mstride() { return MAT_BYTES + (INTERLEAVE ? 128 * INVGPU_TMA_STAGGER : 0); }
     template <bool INTERLEAVE> __host__ __device__ static constexpr size_t smem() {
         return (size_t)WARPS * (INTERLEAVE ? (MPW * mstride<INTERLEAVE>() + 1023) / 1024 * 1024 : MPW * mstride<INTERLEAVE>()) +
                (size_t)SG::MPB * SG::WORDS * sizeof(T) + WARPS * 8;
@@ -904,7 +907,7 @@ struct SweepTmaGeo {
     // (the warp's first buffer is 1024-byte aligned; j shifts the swizzle phase only in the interleaved layout)
     template <bool INTERLEAVE>
     static __device__ __forceinline__ int off(int chunk, int col, int j) {
-        return col * 128 + ((chunk ^ ((col + (INTERLEAVE ? j : 0)) & 7)) << 4);
+        return col * 128 + ((chunk ^ ((col + (INTERLEAVE ? INVGPU_TMA_STAGGER * j : 0)) & 7)) << 4);
     }
 };
 
@@ -1096,6 +1099,135 @@ sweep_spd_tma_kernel(const __grid_constant__ TmaMaps maps, const T *__restrict__
         __syncwarp();
     }
     if (wl == 0) tma_store_wait_all();                             // global writes complete before the CTA retires
+}
+
+// ==========================================================================================
+// n = 8: ONE THREAD PER MATRIX, the whole sweep in registers, TMA tile I/O.
+//
+// An 8x8 matrix is 36 lower-triangle values: a thread sweeps it with static register indices and no
+// shared-memory traffic at all, so the kernel is pure data movement -- which is the hard part when every
+// lane owns a 256-byte matrix: direct 16-byte accesses touch 32 different lines per instruction.  Here a
+// warp tile (32 consecutive matrices, 8 KB fp32 / 16 KB fp64) is one `cp.async.bulk.tensor.2d` into a
+// 128-byte-swizzled box (2-way conflicts for the per-lane reads instead of 8-way), results go back through
+// the same box with one bulk store, and two boxes per warp alternate so that the load of tile i+1 and the
+// store of tile i-1 overlap the arithmetic of tile i.  Pivots in natural order: `info` is spotrf's directly.
+// ==========================================================================================
+template <typename T, int NBUF>
+struct Small8Geo {
+    static constexpr int N = 8;
+    static constexpr int WARPS = 4, BLOCK = 32 * WARPS, MPB = 32 * WARPS;
+    static constexpr int MAT_BYTES = 64 * (int)sizeof(T);
+    static constexpr int BOX_BYTES = 32 * MAT_BYTES;               // 32 matrices
+    static constexpr int LINES_PER_MAT = MAT_BYTES / 128;          // 2 (fp32) or 4 (fp64)
+    static constexpr int EPC = 16 / (int)sizeof(T);                // elements per 16-byte chunk
+    static constexpr size_t SMEM = (size_t)WARPS * NBUF * BOX_BYTES + WARPS * 2 * 8;
+    // byte offset inside the (1024-byte aligned) box of the chunk holding rows r .. r+EPC-1 of column c of lane l's matrix
+    static __device__ __forceinline__ int off(int l, int c, int r) {
+        const int byte = l * MAT_BYTES + (c * 8 + r) * (int)sizeof(T);
+        const int line = byte >> 7, chunk = (byte >> 4) & 7;
+        return (line << 7) + ((chunk ^ (line & 7)) << 4);
+    }
+};
+
+template <typename T, int NBUF, int MINB>
+__global__ void __launch_bounds__((Small8Geo<T, NBUF>::BLOCK), MINB)
+spd8_tma_kernel(const __grid_constant__ TmaMaps maps, const T *__restrict__ in, T *__restrict__ out, i64 batch, int *__restrict__ info) {
+    using G = Small8Geo<T, NBUF>;
+    constexpr int N = 8, EPC = G::EPC;
+    extern __shared__ __align__(1024) unsigned char smem_raw_s8[];
+    const int warp = threadIdx.x >> 5, l = threadIdx.x & 31;
+    unsigned char *boxes = smem_raw_s8 + (size_t)warp * NBUF * G::BOX_BYTES;
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem_raw_s8 + (size_t)G::WARPS * NBUF * G::BOX_BYTES) + 2 * warp;
+    if ((smem_u32(smem_raw_s8) & 1023u) != 0) __trap();
+    if (l == 0) {
+        mbar_init(bars, 1); mbar_init(bars + 1, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const i64 ntiles = (batch + 31) / 32;
+    const i64 tstride = (i64)gridDim.x * G::WARPS;
+    i64 tile = (i64)blockIdx.x * G::WARPS + warp;
+    constexpr int LPT = 32 * G::LINES_PER_MAT;                     // 128-byte lines per warp tile
+    if (tile < ntiles && l == 0) {
+        mbar_expect_tx(bars, G::BOX_BYTES);
+        tma_load_2d(boxes, &maps.in, 0, (int)(tile * LPT), bars);
+    }
+    unsigned phase0 = 0, phase1 = 0;
+    int cur = 0;
+    #pragma unroll 1
+    for (; tile < ntiles; tile += tstride, cur ^= (NBUF - 1)) {
+        unsigned char *box = boxes + cur * G::BOX_BYTES;
+        // two boxes: the other one still feeds the bulk store of the previous tile: wait for that read, then prefetch into it
+        if (NBUF == 2 && l == 0) {
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            if (tile + tstride < ntiles) {
+                mbar_expect_tx(bars + (cur ^ 1), G::BOX_BYTES);
+                tma_load_2d(boxes + (cur ^ 1) * G::BOX_BYTES, &maps.in, 0, (int)((tile + tstride) * LPT), bars + (cur ^ 1));
+            }
+        }
+        if (cur == 0) { mbar_wait(bars, phase0); phase0 ^= 1; } else { mbar_wait(bars + 1, phase1); phase1 ^= 1; }
+        const i64 m = tile * 32 + l;
+        const bool valid = m < batch;
+
+        // ---- upper triangle -> registers (t[i][c], i >= c, = -A(c, i))
+        T t[N][N];
+        #pragma unroll
+        for (int c = 0; c < N; ++c)
+            #pragma unroll
+            for (int r = 0; r <= c; r += EPC) {
+                const T *p = reinterpret_cast<const T *>(box + G::off(l, c, r));
+                #pragma unroll
+                for (int e = 0; e < EPC; ++e)
+                    if (r + e <= c) t[c][r + e] = -p[e];
+            }
+        // ---- the sweep: T = -A -> A^-1, natural pivot order, everything in registers
+        int st = 0;
+        #pragma unroll
+        for (int k = 0; k < N; ++k) {
+            const T d = -t[k][k];
+            if (st == 0 && !(d > T(0))) st = k + 1;
+            const T r = dev_rcp_fast<T>(d);
+            T z[N], x[N];
+            #pragma unroll
+            for (int i = 0; i < N; ++i) { z[i] = (i > k) ? t[i][k] : (i < k ? t[k][i] : T(-1)); x[i] = r * z[i]; }
+            #pragma unroll
+            for (int i = 0; i < N; ++i)
+                #pragma unroll
+                for (int c = 0; c <= i; ++c) {
+                    if (i == k || c == k) t[i][c] = x[i] * z[c];   // restarted slots: column / row k and the pivot
+                    else t[i][c] = fma(x[i], z[c], t[i][c]);
+                }
+        }
+        if (valid && info) info[m] = st;
+        // ---- both triangles -> box (NaN for a flagged matrix)
+        #pragma unroll
+        for (int c = 0; c < N; ++c)
+            #pragma unroll
+            for (int r = 0; r < N; r += EPC) {
+                T *p = reinterpret_cast<T *>(box + G::off(l, c, r));
+                #pragma unroll
+                for (int e = 0; e < EPC; ++e) {
+                    const int rr = r + e;
+                    p[e] = st ? dev_nan<T>() : (rr >= c ? t[rr][c] : t[c][rr]);
+                }
+            }
+        fence_proxy_async();
+        __syncwarp();
+        if (l == 0) {
+            tma_store_2d(&maps.out, 0, (int)(tile * LPT), box);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            if (NBUF == 1) {                                       // one box: reload it as soon as the store has read it
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                if (tile + tstride < ntiles) {
+                    mbar_expect_tx(bars, G::BOX_BYTES);
+                    tma_load_2d(box, &maps.in, 0, (int)((tile + tstride) * LPT), bars);
+                }
+            }
+        }
+        if (NBUF == 1) __syncwarp();
+    }
+    if (l == 0) tma_store_wait_all();
 }
 
 }  // namespace invgpu

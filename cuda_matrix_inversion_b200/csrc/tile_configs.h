@@ -90,7 +90,10 @@
 // INVGPU_SWEEP_VARIANT=9 skips the TMA kernels), TMA in + out 0.508 (6), TMA in with prefetch + direct stores 0.507 (7), TMA in + out with INTERLEAVED
 // lanes 0.577 (0, the default; direct stores with interleaved lanes: 0.448, 4 x 2 lanes interleaved: 0.456): the kernel is bound by shared-memory bandwidth, and with the global side on the TMA
 // unit the lane map can be chosen for the publish stores alone.
-#define INVGPU_SWEEP_TMA_F32(X) X(0, float, 32, 2, 4, false, 3, false, true) X(6, float, 32, 2, 4, false, 3, false, false) X(7, float, 32, 2, 4, false, 3, true, false)
+#ifndef INVGPU_TMA_N32_MINB
+#define INVGPU_TMA_N32_MINB 3
+#endif
+#define INVGPU_SWEEP_TMA_F32(X) X(0, float, 32, 2, 4, false, INVGPU_TMA_N32_MINB, false, true) X(6, float, 32, 2, 4, false, 3, false, false) X(7, float, 32, 2, 4, false, 3, true, false)
 #define INVGPU_SWEEP_TMA_F64(X)
 #define INVGPU_SWEEP_TMA_ALL(X) INVGPU_SWEEP_TMA_F32(X) INVGPU_SWEEP_TMA_F64(X)
 
@@ -117,3 +120,8 @@
 #define INVGPU_GJT_F32(X) X(float, 64, 8, 4, 3) X(float, 128, 4, 32, 3)
 #define INVGPU_GJT_F64(X) X(double, 32, 4, 4, 2) X(double, 64, 8, 8, 4) X(double, 128, 16, 16, 1)
 #define INVGPU_GJT_ALL(X) INVGPU_GJT_F32(X) INVGPU_GJT_F64(X)
+
+// n = 8: one thread per matrix, sweep in registers, TMA tile I/O (spd8_tma_kernel):  X(T, NBUF, MINB)
+#define INVGPU_SPD8_TMA_F32(X) X(float, 2, 3)
+#define INVGPU_SPD8_TMA_F64(X) X(double, 1, 3)
+#define INVGPU_SPD8_TMA_ALL(X) INVGPU_SPD8_TMA_F32(X) INVGPU_SPD8_TMA_F64(X)

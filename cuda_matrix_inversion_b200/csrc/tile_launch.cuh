@@ -36,6 +36,9 @@ int launch_sweep_pad(PadIO<T> io, i64 batch, int *dInfo, cudaStream_t st, Device
 template <typename T, int N, int TR, int TC, bool UNROLL, int MINB, bool DIRECT_OUT, bool INTERLEAVE>
 int launch_sweep_tma(StridedIO<T> io, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds);
 
+template <typename T, int NBUF, int MINB>
+int launch_spd8_tma(StridedIO<T> io, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds);
+
 }  // namespace invgpu
 
 #ifdef INVGPU_TILE_DEFINE
@@ -111,6 +114,48 @@ static int make_batch_tensor_map(void *out128, const T *base, i64 batch, int mat
     if (r != CUDA_SUCCESS) return INVGPU_TMA_UNAVAILABLE;
     memcpy(out128, &m, 128);
     return 0;
+}
+
+// any dense batch as a 2-D tensor of 128-byte lines, box = `box_lines` lines, 128-byte swizzle
+template <typename T>
+static int make_lines_tensor_map(void *out128, const T *base, i64 total_lines, int box_lines) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return INVGPU_TMA_UNAVAILABLE;
+    constexpr int EPL = 128 / (int)sizeof(T);
+    const cuuint64_t dims[2] = {(cuuint64_t)EPL, (cuuint64_t)total_lines};
+    const cuuint64_t strides[1] = {128};
+    const cuuint32_t box[2] = {(cuuint32_t)EPL, (cuuint32_t)box_lines};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUtensorMapDataType dt = sizeof(T) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64;
+    CUtensorMap m;
+    const CUresult r = enc(&m, dt, 2, const_cast<T *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return INVGPU_TMA_UNAVAILABLE;
+    memcpy(out128, &m, 128);
+    return 0;
+}
+
+template <typename T, int NBUF, int MINB>
+int launch_spd8_tma(StridedIO<T> io, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds) {
+    using G = Small8Geo<T, NBUF>;
+    if (io.in_stride != 64 || io.out_stride != 64) return INVGPU_TMA_UNAVAILABLE;
+    const i64 lines = batch * G::LINES_PER_MAT;
+    if (lines > 0x7fffffffLL) return INVGPU_TMA_UNAVAILABLE;
+    TmaMaps maps;
+    int rc = make_lines_tensor_map<T>(maps.in, io.in, lines, 32 * G::LINES_PER_MAT);
+    if (rc) return rc;
+    rc = make_lines_tensor_map<T>(maps.out, io.out, lines, 32 * G::LINES_PER_MAT);
+    if (rc) return rc;
+    auto kern = spd8_tma_kernel<T, NBUF, MINB>;
+    int grid = 0;
+    rc = persistent_grid(kern, G::BLOCK, G::SMEM, (batch + G::MPB - 1) / G::MPB, ds, &grid);
+    if (rc) return rc;
+    static int trace = -1;
+    if (trace < 0) { const char *e = getenv("INVGPU_TRACE"); trace = (e && atoi(e) > 0) ? 1 : 0; }
+    if (trace) fprintf(stderr, "[invgpu] spd8_tma_kernel<%s, nbuf=%d> grid %d smem %zu\n", sizeof(T) == 4 ? "f32" : "f64", NBUF, grid, (size_t)G::SMEM);
+    kern<<<grid, G::BLOCK, G::SMEM, st>>>(maps, io.in, io.out, batch, dInfo);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return (int)cudaGetLastError();
 }
 
 template <typename T, int N, int TR, int TC, bool UNROLL, int MINB, bool DIRECT_OUT, bool INTERLEAVE>
@@ -252,6 +297,8 @@ int launch_tile_gp(GpIO<T> io, i64 batch, int *dInfo, cudaStream_t st, DeviceSta
     template int invgpu::launch_gj_tile<T, N, TR, TC, invgpu::PtrIO<T>, MINB>(invgpu::PtrIO<T>, int, invgpu::i64, int *, cudaStream_t, invgpu::DeviceState *);
 #define INVGPU_ONESWEEP_INSTANTIATE(T, N, TR, TC, STAGE, MINB) \
     template int invgpu::launch_onesweep<T, N, TR, TC, STAGE, MINB>(invgpu::StridedIO<T>, invgpu::i64, int *, cudaStream_t, invgpu::DeviceState *);
+#define INVGPU_SPD8_TMA_INSTANTIATE(T, NBUF, MINB) \
+    template int invgpu::launch_spd8_tma<T, NBUF, MINB>(invgpu::StridedIO<T>, invgpu::i64, int *, cudaStream_t, invgpu::DeviceState *);
 #define INVGPU_SWEEP_TMA_INSTANTIATE(V, T, N, TR, TC, UNROLL, MINB, DIRECT_OUT, INTERLEAVE) \
     template int invgpu::launch_sweep_tma<T, N, TR, TC, UNROLL, MINB, DIRECT_OUT, INTERLEAVE>(invgpu::StridedIO<T>, invgpu::i64, int *, cudaStream_t, invgpu::DeviceState *);
 #define INVGPU_SWEEP_PAD_INSTANTIATE(T, N, TR, TC, MINB) \

@@ -199,6 +199,7 @@ def _extras(torch, api, steps, warmup, hbm_peak):
         del a, o
 
     inv_case("spd_8_f32", 8, 1 << 22, f32)
+    inv_case("spd_8_f64", 8, 1 << 21, f64)
     inv_case("spd_16_f32", 16, 1 << 21, f32)
     inv_case("spd_32_f64", 32, 1 << 19, f64)
     inv_case("spd_64_f32", 64, 1 << 17, f32)

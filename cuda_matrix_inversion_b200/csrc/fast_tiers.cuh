@@ -74,6 +74,12 @@ static int fast_spd_dense(StridedIO<T> io, int n, i64 batch, int *dInfo, cudaStr
             }
             INVGPU_SPD8_TMA_ALL(INVGPU_SPD8_TRY)
         }
+        if (!old && variant != 9) {                                // one thread per matrix + per-lane bulk copies
+#define INVGPU_THREAD_BULK_TRY(TT, N, WARPS, MINB)                                                   \
+            if (std::is_same<T, TT>::value && n == N)                                                 \
+                return launch_spd_thread_bulk<TT, N, WARPS, MINB>(*reinterpret_cast<StridedIO<TT> *>(&io), batch, dInfo, st, ds);
+            INVGPU_THREAD_BULK_ALL(INVGPU_THREAD_BULK_TRY)
+        }
         if (!old && n >= INVGPU_SWEEP_MIN_N) {
             if (variant == 9) variant = 0;                         // 9 = the default grids without TMA tile I/O
             else { INVGPU_SWEEP_TMA_ALL(INVGPU_SWEEP_TMA_TRY) }    // falls through when the batch is not TMA-describable
@@ -205,6 +211,8 @@ static int fast_padded(PadIO<T> io, int tier_n, i64 batch, int *dInfo, cudaStrea
     if (op == 1 && n > INVGPU_GJT_MIN_N(TT) && n <= N && dtype_bytes == (int)sizeof(TT)) return TR * TC <= 32 ? "gj-tile-warp" : "gj-tile-cta";
 #define INVGPU_GJ_NAME(TT, N, ROWS, MINB) \
     if (op == 1 && n <= N && dtype_bytes == (int)sizeof(TT)) return "warp-rowlane";
+#define INVGPU_THREAD_BULK_NAME(TT, N, WARPS, MINB) \
+    if (op == 0 && n == N && dtype_bytes == (int)sizeof(TT)) return "thread-bulk";
 #define INVGPU_SPD8_NAME(TT, NBUF, MINB) \
     if (op == 0 && n == 8 && dtype_bytes == (int)sizeof(TT)) return "thread-tma";
 #define INVGPU_SWEEP_NAME(V, TT, N, TR, TC, UNROLL, MINB, BLK) \
@@ -213,6 +221,7 @@ static int fast_padded(PadIO<T> io, int tier_n, i64 batch, int *dInfo, cudaStrea
     if (op == 2 && V == 0 && n == N && dtype_bytes == (int)sizeof(TT)) return TR * TC <= 32 ? "sweep-warp" : "sweep-cta";
 static const char *fast_tier_name(int op, int n, int dtype_bytes) {
     INVGPU_SPD8_TMA_ALL(INVGPU_SPD8_NAME)
+    INVGPU_THREAD_BULK_ALL(INVGPU_THREAD_BULK_NAME)
     INVGPU_SWEEP_ALL(INVGPU_SWEEP_NAME)
     INVGPU_SWEEP_GP_ALL(INVGPU_SWEEP_GP_NAME)
     INVGPU_GJT_ALL(INVGPU_GJT_NAME)

@@ -1230,4 +1230,111 @@ spd8_tma_kernel(const __grid_constant__ TmaMaps maps, const T *__restrict__ in, 
     if (l == 0) tma_store_wait_all();
 }
 
+// ==========================================================================================
+// n = 16 fp32: one thread per matrix as above (136 lower-triangle values in registers), but the matrices
+// of a warp are 1 KB apart, which defeats the 128-byte swizzle (all lanes would hit the same banks).
+// Every lane therefore moves ITS matrix with a 1-D bulk copy (`cp.async.bulk`, no tensor map) into a slot
+// that is 16 bytes longer than the matrix: consecutive lanes start one bank group further and the per-lane
+// 16-byte accesses are conflict-free.  One mbarrier per warp collects the 32 copies; every lane stores its
+// own result with a bulk copy of its own group.
+// ==========================================================================================
+template <typename T, int N, int WARPS>
+struct ThreadBulkGeo {
+    static constexpr int BLOCK = 32 * WARPS, MPB = 32 * WARPS;
+    static constexpr int MAT_BYTES = N * N * (int)sizeof(T);
+    static constexpr int SLOT = MAT_BYTES + 16;
+    static constexpr int EPC = 16 / (int)sizeof(T);
+    static constexpr size_t SMEM = (size_t)WARPS * 32 * SLOT + WARPS * 8 + 16;
+};
+
+__device__ __forceinline__ void bulk_load_1d(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_store_1d(void *dst, const void *src, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+}
+
+template <typename T, int N, int WARPS, int MINB>
+__global__ void __launch_bounds__((ThreadBulkGeo<T, N, WARPS>::BLOCK), MINB)
+spd_thread_bulk_kernel(const T *__restrict__ in, i64 in_stride, T *__restrict__ out, i64 out_stride, i64 batch, int *__restrict__ info) {
+    using G = ThreadBulkGeo<T, N, WARPS>;
+    constexpr int EPC = G::EPC;
+    extern __shared__ __align__(16) unsigned char smem_raw_tb[];
+    const int warp = threadIdx.x >> 5, l = threadIdx.x & 31;
+    unsigned char *slot = smem_raw_tb + ((size_t)warp * 32 + l) * G::SLOT;
+    unsigned long long *bar = reinterpret_cast<unsigned long long *>(smem_raw_tb + (((size_t)WARPS * 32 * G::SLOT + 15) & ~(size_t)15)) + warp;
+    if (l == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const i64 ntiles = (batch + 31) / 32;
+    const i64 tstride = (i64)gridDim.x * WARPS;
+    i64 tile = (i64)blockIdx.x * WARPS + warp;
+    auto issue = [&](i64 t) {                                      // all lanes: lane 0 arms, every valid lane copies its matrix
+        const i64 m = t * 32 + l;
+        const i64 left = batch - t * 32;
+        if (l == 0) mbar_expect_tx(bar, (unsigned)((left < 32 ? left : 32) * G::MAT_BYTES));
+        __syncwarp();
+        if (m < batch) bulk_load_1d(slot, in + m * in_stride, G::MAT_BYTES, bar);
+    };
+    if (tile < ntiles) issue(tile);
+    unsigned phase = 0;
+    #pragma unroll 1
+    for (; tile < ntiles; tile += tstride) {
+        const i64 m = tile * 32 + l;
+        const bool valid = m < batch;
+        mbar_wait(bar, phase);
+        phase ^= 1;
+
+        T t[N][N];                                                 // t[i][c], i >= c, = -A(c, i) (upper triangle of the input)
+        #pragma unroll
+        for (int c = 0; c < N; ++c)
+            #pragma unroll
+            for (int r = 0; r <= c; r += EPC) {
+                const T *p = reinterpret_cast<const T *>(slot + (c * N + r) * (int)sizeof(T));
+                #pragma unroll
+                for (int e = 0; e < EPC; ++e)
+                    if (r + e <= c) t[c][r + e] = -p[e];
+            }
+        int st = 0;
+        #pragma unroll
+        for (int k = 0; k < N; ++k) {
+            const T d = -t[k][k];
+            if (st == 0 && !(d > T(0))) st = k + 1;
+            const T r = dev_rcp_fast<T>(d);
+            T z[N], x[N];
+            #pragma unroll
+            for (int i = 0; i < N; ++i) { z[i] = (i > k) ? t[i][k] : (i < k ? t[k][i] : T(-1)); x[i] = r * z[i]; }
+            #pragma unroll
+            for (int i = 0; i < N; ++i)
+                #pragma unroll
+                for (int c = 0; c <= i; ++c) {
+                    if (i == k || c == k) t[i][c] = x[i] * z[c];
+                    else t[i][c] = fma(x[i], z[c], t[i][c]);
+                }
+        }
+        if (valid && info) info[m] = st;
+        #pragma unroll
+        for (int c = 0; c < N; ++c)
+            #pragma unroll
+            for (int r = 0; r < N; r += EPC) {
+                T *p = reinterpret_cast<T *>(slot + (c * N + r) * (int)sizeof(T));
+                #pragma unroll
+                for (int e = 0; e < EPC; ++e) {
+                    const int rr = r + e;
+                    p[e] = st ? dev_nan<T>() : (rr >= c ? t[rr][c] : t[c][rr]);
+                }
+            }
+        fence_proxy_async();
+        if (valid) bulk_store_1d(out + m * out_stride, slot, G::MAT_BYTES);
+        asm volatile("cp.async.bulk.commit_group;\n\tcp.async.bulk.wait_group.read 0;" ::: "memory");   // own slot read: reusable
+        __syncwarp();
+        if (tile + tstride < ntiles) issue(tile + tstride);
+    }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 }  // namespace invgpu

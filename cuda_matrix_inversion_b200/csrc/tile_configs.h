@@ -125,3 +125,8 @@
 #define INVGPU_SPD8_TMA_F32(X) X(float, 2, 3)
 #define INVGPU_SPD8_TMA_F64(X) X(double, 1, 3)
 #define INVGPU_SPD8_TMA_ALL(X) INVGPU_SPD8_TMA_F32(X) INVGPU_SPD8_TMA_F64(X)
+
+// one thread per matrix with per-lane 1-D bulk copies into padded slots (spd_thread_bulk_kernel):  X(T, N, WARPS, MINB)
+#define INVGPU_THREAD_BULK_F32(X) X(float, 16, 2, 3)
+#define INVGPU_THREAD_BULK_F64(X)
+#define INVGPU_THREAD_BULK_ALL(X) INVGPU_THREAD_BULK_F32(X) INVGPU_THREAD_BULK_F64(X)

@@ -39,6 +39,9 @@ int launch_sweep_tma(StridedIO<T> io, i64 batch, int *dInfo, cudaStream_t st, De
 template <typename T, int NBUF, int MINB>
 int launch_spd8_tma(StridedIO<T> io, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds);
 
+template <typename T, int N, int WARPS, int MINB>
+int launch_spd_thread_bulk(StridedIO<T> io, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds);
+
 }  // namespace invgpu
 
 #ifdef INVGPU_TILE_DEFINE
@@ -133,6 +136,18 @@ static int make_lines_tensor_map(void *out128, const T *base, i64 total_lines, i
     if (r != CUDA_SUCCESS) return INVGPU_TMA_UNAVAILABLE;
     memcpy(out128, &m, 128);
     return 0;
+}
+
+template <typename T, int N, int WARPS, int MINB>
+int launch_spd_thread_bulk(StridedIO<T> io, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds) {
+    using G = ThreadBulkGeo<T, N, WARPS>;
+    auto kern = spd_thread_bulk_kernel<T, N, WARPS, MINB>;
+    int grid = 0;
+    int rc = persistent_grid(kern, G::BLOCK, G::SMEM, (batch + G::MPB - 1) / G::MPB, ds, &grid);
+    if (rc) return rc;
+    kern<<<grid, G::BLOCK, G::SMEM, st>>>(io.in, io.in_stride, io.out, io.out_stride, batch, dInfo);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return (int)cudaGetLastError();
 }
 
 template <typename T, int NBUF, int MINB>
@@ -297,6 +312,8 @@ int launch_tile_gp(GpIO<T> io, i64 batch, int *dInfo, cudaStream_t st, DeviceSta
     template int invgpu::launch_gj_tile<T, N, TR, TC, invgpu::PtrIO<T>, MINB>(invgpu::PtrIO<T>, int, invgpu::i64, int *, cudaStream_t, invgpu::DeviceState *);
 #define INVGPU_ONESWEEP_INSTANTIATE(T, N, TR, TC, STAGE, MINB) \
     template int invgpu::launch_onesweep<T, N, TR, TC, STAGE, MINB>(invgpu::StridedIO<T>, invgpu::i64, int *, cudaStream_t, invgpu::DeviceState *);
+#define INVGPU_THREAD_BULK_INSTANTIATE(T, N, WARPS, MINB) \
+    template int invgpu::launch_spd_thread_bulk<T, N, WARPS, MINB>(invgpu::StridedIO<T>, invgpu::i64, int *, cudaStream_t, invgpu::DeviceState *);
 #define INVGPU_SPD8_TMA_INSTANTIATE(T, NBUF, MINB) \
     template int invgpu::launch_spd8_tma<T, NBUF, MINB>(invgpu::StridedIO<T>, invgpu::i64, int *, cudaStream_t, invgpu::DeviceState *);
 #define INVGPU_SWEEP_TMA_INSTANTIATE(V, T, N, TR, TC, UNROLL, MINB, DIRECT_OUT, INTERLEAVE) \

@@ -619,7 +619,7 @@ print("variant ok", err)
 """
 
 
-@pytest.mark.parametrize("variant,n", [(0, 32), (6, 32), (7, 32), (9, 32), (4, 32), (4, 64), (4, 128), (1, 32), (3, 64), (3, 128)])
+@pytest.mark.parametrize("variant,n", [(0, 32), (6, 32), (7, 32), (9, 32), (9, 8), (9, 16), (4, 32), (4, 64), (4, 128), (1, 32), (3, 64), (3, 128)])
 def test_sweep_kernel_variants(variant, n):
     """The non-default sweep configurations (n = 32: 0 = default = TMA tile I/O with interleaved lanes, 6 = TMA without
     interleaving, 7 = TMA load with prefetch + direct stores, 9 = direct global access; 2x2 block pivots: 4; other grids) are selected

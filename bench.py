@@ -205,6 +205,7 @@ def _extras(torch, api, steps, warmup, hbm_peak):
     inv_case("spd_64_f32", 64, 1 << 17, f32)
     inv_case("spd_64_f64", 64, 1 << 16, f64)
     inv_case("spd_128_f32", 128, 1 << 15, f32)
+    inv_case("gauss_jordan_8_f32", 8, 1 << 22, f32, general=True)
     inv_case("gauss_jordan_32_f32", 32, 1 << 17, f32, general=True)
     inv_case("gauss_jordan_64_f32", 64, 1 << 15, f32, general=True)
     inv_case("gauss_jordan_128_f32", 128, 1 << 13, f32, general=True)

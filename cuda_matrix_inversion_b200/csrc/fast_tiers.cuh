@@ -69,7 +69,7 @@ static int fast_spd_dense(StridedIO<T> io, int n, i64 batch, int *dInfo, cudaStr
         if (!old && n == 8 && variant != 9) {                      // one thread per matrix + TMA tile I/O
 #define INVGPU_SPD8_TRY(TT, NBUF, MINB)                                                              \
             if (std::is_same<T, TT>::value) {                                                         \
-                const int rc8 = launch_spd8_tma<TT, NBUF, MINB>(*reinterpret_cast<StridedIO<TT> *>(&io), batch, dInfo, st, ds); \
+                const int rc8 = launch_spd8_tma<TT, NBUF, MINB, false>(*reinterpret_cast<StridedIO<TT> *>(&io), batch, dInfo, st, ds); \
                 if (rc8 != INVGPU_TMA_UNAVAILABLE) return rc8;                                         \
             }
             INVGPU_SPD8_TMA_ALL(INVGPU_SPD8_TRY)
@@ -165,6 +165,16 @@ static int fast_general(IO io, int n, i64 batch, int *dInfo, cudaStream_t st, De
         which = (e && !strcmp(e, "rowlane")) ? 1 : (e && !strcmp(e, "generic")) ? 2 : 0;
     }
     if (which == 2) return INVGPU_NO_FAST_PATH;
+    if constexpr (std::is_same<IO, StridedIO<T>>::value) {        // dense batches of order exactly 8: one thread per matrix + TMA
+        if (which == 0 && n == 8 && dense_aligned(io, 8)) {
+#define INVGPU_GJ8_TRY(TT, NBUF, MINB)                                                               \
+            if (std::is_same<T, TT>::value) {                                                         \
+                const int rc8 = launch_spd8_tma<TT, NBUF, MINB, true>(*reinterpret_cast<StridedIO<TT> *>(&io), batch, dInfo, st, ds); \
+                if (rc8 != INVGPU_TMA_UNAVAILABLE) return rc8;                                         \
+            }
+            INVGPU_SPD8_TMA_ALL(INVGPU_GJ8_TRY)
+        }
+    }
     if (which == 0 && n > INVGPU_GJT_MIN_N(T)) { INVGPU_GJT_ALL(INVGPU_GJT_TRY) }
     INVGPU_GJ_ALL(INVGPU_GJ_TRY)
     return INVGPU_NO_FAST_PATH;
@@ -207,6 +217,8 @@ static int fast_padded(PadIO<T> io, int tier_n, i64 batch, int *dInfo, cudaStrea
     if (op == 0 && n == N && dtype_bytes == (int)sizeof(TT) && STAGES_ == 7) return TR * TC <= 32 ? "warp-tile" : "cta-tile";
 #define INVGPU_TILE_NAME_GP(TT, N, TR, TC, MINB) \
     if (op == 2 && n == N && dtype_bytes == (int)sizeof(TT)) return TR * TC <= 32 ? "warp-tile" : "cta-tile";
+#define INVGPU_GJ8_NAME(TT, NBUF, MINB) \
+    if (op == 1 && n == 8 && dtype_bytes == (int)sizeof(TT)) return "thread-tma";
 #define INVGPU_GJT_NAME(TT, N, TR, TC, MINB) \
     if (op == 1 && n > INVGPU_GJT_MIN_N(TT) && n <= N && dtype_bytes == (int)sizeof(TT)) return TR * TC <= 32 ? "gj-tile-warp" : "gj-tile-cta";
 #define INVGPU_GJ_NAME(TT, N, ROWS, MINB) \
@@ -224,6 +236,7 @@ static const char *fast_tier_name(int op, int n, int dtype_bytes) {
     INVGPU_THREAD_BULK_ALL(INVGPU_THREAD_BULK_NAME)
     INVGPU_SWEEP_ALL(INVGPU_SWEEP_NAME)
     INVGPU_SWEEP_GP_ALL(INVGPU_SWEEP_GP_NAME)
+    INVGPU_SPD8_TMA_ALL(INVGPU_GJ8_NAME)
     INVGPU_GJT_ALL(INVGPU_GJT_NAME)
     INVGPU_GJ_ALL(INVGPU_GJ_NAME)
     INVGPU_TILE_SPD_ALL(INVGPU_TILE_NAME)

@@ -1129,7 +1129,137 @@ struct Small8Geo {
     }
 };
 
-template <typename T, int NBUF, int MINB>
+// per-thread arithmetic on the matrix of lane l inside the swizzled box: read it, transform it in registers, write
+// the result back into the box; returns LAPACK's info
+template <typename T>
+struct Spd8Math {                                                  // SPD inverse: symmetric sweep on the lower triangle
+    template <typename G>
+    static __device__ __forceinline__ int apply(unsigned char *box, int l) {
+        constexpr int N = 8, EPC = G::EPC;
+        // ---- upper triangle -> registers (t[i][c], i >= c, = -A(c, i))
+        T t[N][N];
+        #pragma unroll
+        for (int c = 0; c < N; ++c)
+            #pragma unroll
+            for (int r = 0; r <= c; r += EPC) {
+                const T *p = reinterpret_cast<const T *>(box + G::off(l, c, r));
+                #pragma unroll
+                for (int e = 0; e < EPC; ++e)
+                    if (r + e <= c) t[c][r + e] = -p[e];
+            }
+        // ---- the sweep: T = -A -> A^-1, natural pivot order, everything in registers
+        int st = 0;
+        #pragma unroll
+        for (int k = 0; k < N; ++k) {
+            const T d = -t[k][k];
+            if (st == 0 && !(d > T(0))) st = k + 1;
+            const T r = dev_rcp_fast<T>(d);
+            T z[N], x[N];
+            #pragma unroll
+            for (int i = 0; i < N; ++i) { z[i] = (i > k) ? t[i][k] : (i < k ? t[k][i] : T(-1)); x[i] = r * z[i]; }
+            #pragma unroll
+            for (int i = 0; i < N; ++i)
+                #pragma unroll
+                for (int c = 0; c <= i; ++c) {
+                    if (i == k || c == k) t[i][c] = x[i] * z[c];   // restarted slots: column / row k and the pivot
+                    else t[i][c] = fma(x[i], z[c], t[i][c]);
+                }
+        }
+        // ---- both triangles -> box (NaN for a flagged matrix)
+        #pragma unroll
+        for (int c = 0; c < N; ++c)
+            #pragma unroll
+            for (int r = 0; r < N; r += EPC) {
+                T *p = reinterpret_cast<T *>(box + G::off(l, c, r));
+                #pragma unroll
+                for (int e = 0; e < EPC; ++e) {
+                    const int rr = r + e;
+                    p[e] = st ? dev_nan<T>() : (rr >= c ? t[rr][c] : t[c][rr]);
+                }
+            }
+        return st;
+    }
+};
+
+// General inverse of an 8x8 matrix: in-place Gauss-Jordan with partial pivoting, rows swapped explicitly by
+// predicated selects (the pivot row index is the only run-time index), columns un-permuted at the end
+// (inv(P A) = A^-1 P^T).  Same arithmetic per element as the oracle / the lane = row kernel (scale the pivot
+// row, then a -= f * row); replaces src/gauss/batched_invert.cu:17-95 for dense batches of order exactly 8.
+template <typename T>
+struct Gj8Math {
+    template <typename G>
+    static __device__ __forceinline__ int apply(unsigned char *box, int l) {
+        constexpr int N = 8, EPC = G::EPC;
+        T a[N][N];                                                 // a[r][c]
+        #pragma unroll
+        for (int c = 0; c < N; ++c)
+            #pragma unroll
+            for (int r = 0; r < N; r += EPC) {
+                const T *p = reinterpret_cast<const T *>(box + G::off(l, c, r));
+                #pragma unroll
+                for (int e = 0; e < EPC; ++e) a[r + e][c] = p[e];
+            }
+        int st = 0;
+        int perm[N];
+        #pragma unroll
+        for (int k = 0; k < N; ++k) {
+            T best = dev_abs(a[k][k]);
+            int p = k;
+            if (!(best >= T(0))) best = T(-1);                     // NaN never wins
+            #pragma unroll
+            for (int r = k + 1; r < N; ++r) {
+                const T v = dev_abs(a[r][k]);
+                if (v > best) { best = v; p = r; }
+            }
+            if (st == 0 && !(best > T(0))) st = k + 1;
+            perm[k] = p;
+            #pragma unroll
+            for (int r = k + 1; r < N; ++r) {                      // swap rows k and p
+                const bool sw = (p == r);
+                #pragma unroll
+                for (int c = 0; c < N; ++c) {
+                    const T u = a[k][c], v = a[r][c];
+                    a[k][c] = sw ? v : u;
+                    a[r][c] = sw ? u : v;
+                }
+            }
+            const T pv = T(1) / a[k][k];
+            #pragma unroll
+            for (int c = 0; c < N; ++c) a[k][c] = (c == k) ? pv : a[k][c] * pv;
+            #pragma unroll
+            for (int r = 0; r < N; ++r) {
+                if (r == k) continue;
+                const T f = a[r][k];
+                #pragma unroll
+                for (int c = 0; c < N; ++c) a[r][c] = (c == k) ? -f * pv : fma(-f, a[k][c], a[r][c]);
+            }
+        }
+        #pragma unroll
+        for (int k = N - 2; k >= 0; --k) {                         // undo the row swaps on the columns, last first
+            #pragma unroll
+            for (int c = k + 1; c < N; ++c) {
+                const bool sw = (perm[k] == c);
+                #pragma unroll
+                for (int r = 0; r < N; ++r) {
+                    const T u = a[r][k], v = a[r][c];
+                    a[r][k] = sw ? v : u;
+                    a[r][c] = sw ? u : v;
+                }
+            }
+        }
+        #pragma unroll
+        for (int c = 0; c < N; ++c)
+            #pragma unroll
+            for (int r = 0; r < N; r += EPC) {
+                T *p = reinterpret_cast<T *>(box + G::off(l, c, r));
+                #pragma unroll
+                for (int e = 0; e < EPC; ++e) p[e] = st ? dev_nan<T>() : a[r + e][c];
+            }
+        return st;
+    }
+};
+
+template <typename T, int NBUF, int MINB, typename MATH = Spd8Math<T>>
 __global__ void __launch_bounds__((Small8Geo<T, NBUF>::BLOCK), MINB)
 spd8_tma_kernel(const __grid_constant__ TmaMaps maps, const T *__restrict__ in, T *__restrict__ out, i64 batch, int *__restrict__ info) {
     using G = Small8Geo<T, NBUF>;
@@ -1170,48 +1300,8 @@ spd8_tma_kernel(const __grid_constant__ TmaMaps maps, const T *__restrict__ in, 
         const i64 m = tile * 32 + l;
         const bool valid = m < batch;
 
-        // ---- upper triangle -> registers (t[i][c], i >= c, = -A(c, i))
-        T t[N][N];
-        #pragma unroll
-        for (int c = 0; c < N; ++c)
-            #pragma unroll
-            for (int r = 0; r <= c; r += EPC) {
-                const T *p = reinterpret_cast<const T *>(box + G::off(l, c, r));
-                #pragma unroll
-                for (int e = 0; e < EPC; ++e)
-                    if (r + e <= c) t[c][r + e] = -p[e];
-            }
-        // ---- the sweep: T = -A -> A^-1, natural pivot order, everything in registers
-        int st = 0;
-        #pragma unroll
-        for (int k = 0; k < N; ++k) {
-            const T d = -t[k][k];
-            if (st == 0 && !(d > T(0))) st = k + 1;
-            const T r = dev_rcp_fast<T>(d);
-            T z[N], x[N];
-            #pragma unroll
-            for (int i = 0; i < N; ++i) { z[i] = (i > k) ? t[i][k] : (i < k ? t[k][i] : T(-1)); x[i] = r * z[i]; }
-            #pragma unroll
-            for (int i = 0; i < N; ++i)
-                #pragma unroll
-                for (int c = 0; c <= i; ++c) {
-                    if (i == k || c == k) t[i][c] = x[i] * z[c];   // restarted slots: column / row k and the pivot
-                    else t[i][c] = fma(x[i], z[c], t[i][c]);
-                }
-        }
+        const int st = MATH::template apply<G>(box, l);
         if (valid && info) info[m] = st;
-        // ---- both triangles -> box (NaN for a flagged matrix)
-        #pragma unroll
-        for (int c = 0; c < N; ++c)
-            #pragma unroll
-            for (int r = 0; r < N; r += EPC) {
-                T *p = reinterpret_cast<T *>(box + G::off(l, c, r));
-                #pragma unroll
-                for (int e = 0; e < EPC; ++e) {
-                    const int rr = r + e;
-                    p[e] = st ? dev_nan<T>() : (rr >= c ? t[rr][c] : t[c][rr]);
-                }
-            }
         fence_proxy_async();
         __syncwarp();
         if (l == 0) {

@@ -36,7 +36,7 @@ int launch_sweep_pad(PadIO<T> io, i64 batch, int *dInfo, cudaStream_t st, Device
 template <typename T, int N, int TR, int TC, bool UNROLL, int MINB, bool DIRECT_OUT, bool INTERLEAVE>
 int launch_sweep_tma(StridedIO<T> io, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds);
 
-template <typename T, int NBUF, int MINB>
+template <typename T, int NBUF, int MINB, bool GENERAL>
 int launch_spd8_tma(StridedIO<T> io, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds);
 
 template <typename T, int N, int WARPS, int MINB>
@@ -46,6 +46,7 @@ int launch_spd_thread_bulk(StridedIO<T> io, i64 batch, int *dInfo, cudaStream_t 
 
 #ifdef INVGPU_TILE_DEFINE
 #include <cuda.h>
+#include <type_traits>
 #include <string.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -150,7 +151,7 @@ int launch_spd_thread_bulk(StridedIO<T> io, i64 batch, int *dInfo, cudaStream_t 
     return (int)cudaGetLastError();
 }
 
-template <typename T, int NBUF, int MINB>
+template <typename T, int NBUF, int MINB, bool GENERAL>
 int launch_spd8_tma(StridedIO<T> io, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds) {
     using G = Small8Geo<T, NBUF>;
     if (io.in_stride != 64 || io.out_stride != 64) return INVGPU_TMA_UNAVAILABLE;
@@ -161,13 +162,13 @@ int launch_spd8_tma(StridedIO<T> io, i64 batch, int *dInfo, cudaStream_t st, Dev
     if (rc) return rc;
     rc = make_lines_tensor_map<T>(maps.out, io.out, lines, 32 * G::LINES_PER_MAT);
     if (rc) return rc;
-    auto kern = spd8_tma_kernel<T, NBUF, MINB>;
+    auto kern = spd8_tma_kernel<T, NBUF, MINB, typename std::conditional<GENERAL, Gj8Math<T>, Spd8Math<T>>::type>;
     int grid = 0;
     rc = persistent_grid(kern, G::BLOCK, G::SMEM, (batch + G::MPB - 1) / G::MPB, ds, &grid);
     if (rc) return rc;
     static int trace = -1;
     if (trace < 0) { const char *e = getenv("INVGPU_TRACE"); trace = (e && atoi(e) > 0) ? 1 : 0; }
-    if (trace) fprintf(stderr, "[invgpu] spd8_tma_kernel<%s, nbuf=%d> grid %d smem %zu\n", sizeof(T) == 4 ? "f32" : "f64", NBUF, grid, (size_t)G::SMEM);
+    if (trace) fprintf(stderr, "[invgpu] spd8_tma_kernel<%s, nbuf=%d, %s> grid %d smem %zu\n", sizeof(T) == 4 ? "f32" : "f64", NBUF, GENERAL ? "gauss-jordan" : "spd", grid, (size_t)G::SMEM);
     kern<<<grid, G::BLOCK, G::SMEM, st>>>(maps, io.in, io.out, batch, dInfo);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return (int)cudaGetLastError();
@@ -315,7 +316,8 @@ int launch_tile_gp(GpIO<T> io, i64 batch, int *dInfo, cudaStream_t st, DeviceSta
 #define INVGPU_THREAD_BULK_INSTANTIATE(T, N, WARPS, MINB) \
     template int invgpu::launch_spd_thread_bulk<T, N, WARPS, MINB>(invgpu::StridedIO<T>, invgpu::i64, int *, cudaStream_t, invgpu::DeviceState *);
 #define INVGPU_SPD8_TMA_INSTANTIATE(T, NBUF, MINB) \
-    template int invgpu::launch_spd8_tma<T, NBUF, MINB>(invgpu::StridedIO<T>, invgpu::i64, int *, cudaStream_t, invgpu::DeviceState *);
+    template int invgpu::launch_spd8_tma<T, NBUF, MINB, false>(invgpu::StridedIO<T>, invgpu::i64, int *, cudaStream_t, invgpu::DeviceState *); \
+    template int invgpu::launch_spd8_tma<T, NBUF, MINB, true>(invgpu::StridedIO<T>, invgpu::i64, int *, cudaStream_t, invgpu::DeviceState *);
 #define INVGPU_SWEEP_TMA_INSTANTIATE(V, T, N, TR, TC, UNROLL, MINB, DIRECT_OUT, INTERLEAVE) \
     template int invgpu::launch_sweep_tma<T, N, TR, TC, UNROLL, MINB, DIRECT_OUT, INTERLEAVE>(invgpu::StridedIO<T>, invgpu::i64, int *, cudaStream_t, invgpu::DeviceState *);
 #define INVGPU_SWEEP_PAD_INSTANTIATE(T, N, TR, TC, MINB) \

@@ -232,9 +232,9 @@ def test_general_inverse_sizes(api, n, dtype):
     assert residual_inf(a, orc.from_colmajor(got, n)) <= 4 * bound
 
 
+@pytest.mark.parametrize("n", [6, 8])                           # 8: the thread-per-matrix kernel (explicit row swaps)
 @pytest.mark.parametrize("dtype", DTYPES)
-def test_general_flags_match_oracle(api, dtype):
-    n = 6
+def test_general_flags_match_oracle(api, dtype, n):
     rng = np.random.default_rng(2)
     a = rng.random((8, n, n)) + np.eye(n)
     a[1, :, 2] = 0.0                 # zero column: pivot 3 is exactly zero

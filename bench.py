@@ -222,6 +222,8 @@ def _extras(torch, api, steps, warmup, hbm_peak):
         out[key] = {"evals_per_s": batch / (ms * 1e-3), "ms": ms, "algorithmic_GBps": gbs,
                     "hbm_frac": gbs / hbm_peak, "tier": api.tier_name("gp", n)}
 
+    gp_case("gp_mean_8_f32", 8, 1 << 22)
+    gp_case("gp_mean_16_f32", 16, 1 << 21)
     gp_case("gp_mean_32_f32", 32, 1 << 19)
     gp_case("gp_mean_64_f32", 64, 100 * 1600)
     gp_case("gp_mean_128_f32_25k", 128, 25000)

@@ -196,6 +196,10 @@ static int fast_gp(GpIO<T> io, int n, i64 batch, int *dInfo, cudaStream_t st, De
     if (old < 0) { const char *e = getenv("INVGPU_GP_KERNEL"); old = (e && !strcmp(e, "tile")) ? 1 : 0; }
     static int variant = -1;                          // INVGPU_SWEEP_VARIANT=V: another instantiated configuration
     if (variant < 0) { const char *e = getenv("INVGPU_SWEEP_VARIANT"); variant = e ? atoi(e) : 0; }
+#define INVGPU_GP_THREAD_TRY(TT, N, WARPS, MINB)                                                    \
+    if (std::is_same<T, TT>::value && n == N)                                                        \
+        return launch_gp_thread<TT, N, WARPS, MINB>(*reinterpret_cast<GpIO<TT> *>(&io), batch, dInfo, st, ds);
+    if (!old) { INVGPU_GP_THREAD_ALL(INVGPU_GP_THREAD_TRY) }
     if (!old) { INVGPU_SWEEP_GP_ALL(INVGPU_SWEEP_TRY_GP) }
     INVGPU_TILE_GP_ALL(INVGPU_TILE_TRY_GP)
     return INVGPU_NO_FAST_PATH;
@@ -229,12 +233,15 @@ static int fast_padded(PadIO<T> io, int tier_n, i64 batch, int *dInfo, cudaStrea
     if (op == 0 && n == 8 && dtype_bytes == (int)sizeof(TT)) return "thread-tma";
 #define INVGPU_SWEEP_NAME(V, TT, N, TR, TC, UNROLL, MINB, BLK) \
     if (op == 0 && V == 0 && n == N && n >= INVGPU_SWEEP_MIN_N && dtype_bytes == (int)sizeof(TT)) return TR * TC <= 32 ? "sweep-warp" : "sweep-cta";
+#define INVGPU_GP_THREAD_NAME(TT, N, WARPS, MINB) \
+    if (op == 2 && n == N && dtype_bytes == (int)sizeof(TT)) return "thread-bulk";
 #define INVGPU_SWEEP_GP_NAME(V, TT, N, TR, TC, UNROLL, MINB, BLK) \
     if (op == 2 && V == 0 && n == N && dtype_bytes == (int)sizeof(TT)) return TR * TC <= 32 ? "sweep-warp" : "sweep-cta";
 static const char *fast_tier_name(int op, int n, int dtype_bytes) {
     INVGPU_SPD8_TMA_ALL(INVGPU_SPD8_NAME)
     INVGPU_THREAD_BULK_ALL(INVGPU_THREAD_BULK_NAME)
     INVGPU_SWEEP_ALL(INVGPU_SWEEP_NAME)
+    INVGPU_GP_THREAD_ALL(INVGPU_GP_THREAD_NAME)
     INVGPU_SWEEP_GP_ALL(INVGPU_SWEEP_GP_NAME)
     INVGPU_SPD8_TMA_ALL(INVGPU_GJ8_NAME)
     INVGPU_GJT_ALL(INVGPU_GJT_NAME)

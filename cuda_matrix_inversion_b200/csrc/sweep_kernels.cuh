@@ -1427,4 +1427,100 @@ spd_thread_bulk_kernel(const T *__restrict__ in, i64 in_stride, T *__restrict__ 
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
+// ==========================================================================================
+// Fused GP mean / variance for tiny matrices (n = 8; n = 16 fp32): ONE THREAD PER EVALUATION.
+// B moves with per-lane 1-D bulk copies into padded slots (as in spd_thread_bulk_kernel); the slot is free as
+// soon as the upper triangle sits in registers, so the copy of the next evaluation is issued before the
+// arithmetic and lands behind it.  diag(C) is added on the way into the registers, the factorisation is
+// A = L D L^T with the two right-hand sides riding along, the scalars are sum u_k v_k / d_k and
+// E - sum u_k^2 / d_k (reference src/gauss_bench.cu:127-265, 275-409 in one launch; nothing but the scalars is
+// written).  Natural pivot order: `info` is spotrf's directly.
+// ==========================================================================================
+template <typename T, int N, int WARPS, int MINB>
+__global__ void __launch_bounds__((ThreadBulkGeo<T, N, WARPS>::BLOCK), MINB)
+gp_thread_kernel(GpIO<T> io, i64 batch, int *__restrict__ info) {
+    using G = ThreadBulkGeo<T, N, WARPS>;
+    constexpr int EPC = G::EPC;
+    extern __shared__ __align__(16) unsigned char smem_raw_gt[];
+    const int warp = threadIdx.x >> 5, l = threadIdx.x & 31;
+    unsigned char *slot = smem_raw_gt + ((size_t)warp * 32 + l) * G::SLOT;
+    unsigned long long *bar = reinterpret_cast<unsigned long long *>(smem_raw_gt + (((size_t)WARPS * 32 * G::SLOT + 15) & ~(size_t)15)) + warp;
+    if (l == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const i64 ntiles = (batch + 31) / 32;
+    const i64 tstride = (i64)gridDim.x * WARPS;
+    i64 tile = (i64)blockIdx.x * WARPS + warp;
+    auto issue = [&](i64 t) {
+        const i64 m = t * 32 + l;
+        const i64 left = batch - t * 32;
+        if (l == 0) mbar_expect_tx(bar, (unsigned)((left < 32 ? left : 32) * G::MAT_BYTES));
+        __syncwarp();
+        if (m < batch) bulk_load_1d(slot, io.b + m * (i64)(N * N), G::MAT_BYTES, bar);
+    };
+    if (tile < ntiles) issue(tile);
+    unsigned phase = 0;
+    #pragma unroll 1
+    for (; tile < ntiles; tile += tstride) {
+        const i64 m = tile * 32 + l;
+        const bool valid = m < batch;
+        const i64 mm = valid ? m : batch - 1;
+        // right-hand sides and the diagonal: N contiguous values per lane, straight from global memory
+        T u[N], v[N], cd[N];
+        {
+            const T *__restrict__ av = io.a + mm * N;
+            const T *__restrict__ dv = (io.d ? io.d : io.a) + mm * N;
+            const T *__restrict__ cv = io.c + mm * N;
+            #pragma unroll
+            for (int i = 0; i < N; i += 4) {
+                ldg4(av + i, u[i], u[i + 1], u[i + 2], u[i + 3]);
+                ldg4(dv + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
+                ldg4(cv + i, cd[i], cd[i + 1], cd[i + 2], cd[i + 3]);
+            }
+        }
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        T t[N][N];                                                 // t[i][c], i >= c, = (B + diag C)(c, i): upper triangle of the input
+        #pragma unroll
+        for (int c = 0; c < N; ++c)
+            #pragma unroll
+            for (int r = 0; r <= c; r += EPC) {
+                const T *p = reinterpret_cast<const T *>(slot + (c * N + r) * (int)sizeof(T));
+                #pragma unroll
+                for (int e = 0; e < EPC; ++e)
+                    if (r + e <= c) t[c][r + e] = p[e] + ((r + e == c) ? cd[c] : T(0));
+            }
+        __syncwarp();                                              // every lane has read its slot
+        if (tile + tstride < ntiles) issue(tile + tstride);        // prefetch under the arithmetic
+
+        int st = 0;
+        T acc_m = T(0), acc_q = T(0);
+        #pragma unroll
+        for (int k = 0; k < N; ++k) {
+            const T d = t[k][k];
+            if (st == 0 && !(d > T(0))) st = k + 1;
+            const T r = dev_rcp_fast<T>(d);
+            const T ur = u[k] * r;
+            acc_m = fma(ur, v[k], acc_m);
+            acc_q = fma(ur, u[k], acc_q);
+            #pragma unroll
+            for (int i = k + 1; i < N; ++i) {
+                const T li = t[i][k] * r;                          // L(i, k)
+                u[i] = fma(-li, u[k], u[i]);
+                v[i] = fma(-li, v[k], v[i]);
+                #pragma unroll
+                for (int c = k + 1; c <= i; ++c) t[i][c] = fma(-li, t[c][k], t[i][c]);
+            }
+        }
+        if (valid) {
+            if (io.means) io.means[m] = st ? dev_nan<T>() : acc_m;
+            if (io.variances) io.variances[m] = st ? dev_nan<T>() : io.e[m] - acc_q;
+            if (info) info[m] = st;
+        }
+    }
+}
+
 }  // namespace invgpu

@@ -37,6 +37,7 @@
     X(float, 64, 8, 4, 3)                                       \
     X(float, 128, 16, 16, 2)
 #define INVGPU_TILE_GP_F64(X)                                   \
+    X(double, 16, 2, 2, 2)                                      \
     X(double, 32, 4, 4, 2)                                      \
     X(double, 64, 8, 8, 4)                                      \
     X(double, 128, 16, 16, 1)
@@ -130,3 +131,8 @@
 #define INVGPU_THREAD_BULK_F32(X) X(float, 16, 2, 3)
 #define INVGPU_THREAD_BULK_F64(X)
 #define INVGPU_THREAD_BULK_ALL(X) INVGPU_THREAD_BULK_F32(X) INVGPU_THREAD_BULK_F64(X)
+
+// fused GP mean / variance, one thread per evaluation (gp_thread_kernel):  X(T, N, WARPS, MINB)
+#define INVGPU_GP_THREAD_F32(X) X(float, 8, 4, 4) X(float, 16, 2, 3)
+#define INVGPU_GP_THREAD_F64(X) X(double, 8, 4, 3)
+#define INVGPU_GP_THREAD_ALL(X) INVGPU_GP_THREAD_F32(X) INVGPU_GP_THREAD_F64(X)

@@ -42,6 +42,9 @@ int launch_spd8_tma(StridedIO<T> io, i64 batch, int *dInfo, cudaStream_t st, Dev
 template <typename T, int N, int WARPS, int MINB>
 int launch_spd_thread_bulk(StridedIO<T> io, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds);
 
+template <typename T, int N, int WARPS, int MINB>
+int launch_gp_thread(GpIO<T> io, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds);
+
 }  // namespace invgpu
 
 #ifdef INVGPU_TILE_DEFINE
@@ -147,6 +150,18 @@ int launch_spd_thread_bulk(StridedIO<T> io, i64 batch, int *dInfo, cudaStream_t 
     int rc = persistent_grid(kern, G::BLOCK, G::SMEM, (batch + G::MPB - 1) / G::MPB, ds, &grid);
     if (rc) return rc;
     kern<<<grid, G::BLOCK, G::SMEM, st>>>(io.in, io.in_stride, io.out, io.out_stride, batch, dInfo);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return (int)cudaGetLastError();
+}
+
+template <typename T, int N, int WARPS, int MINB>
+int launch_gp_thread(GpIO<T> io, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds) {
+    using G = ThreadBulkGeo<T, N, WARPS>;
+    auto kern = gp_thread_kernel<T, N, WARPS, MINB>;
+    int grid = 0;
+    int rc = persistent_grid(kern, G::BLOCK, G::SMEM, (batch + G::MPB - 1) / G::MPB, ds, &grid);
+    if (rc) return rc;
+    kern<<<grid, G::BLOCK, G::SMEM, st>>>(io, batch, dInfo);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return (int)cudaGetLastError();
 }
@@ -313,6 +328,8 @@ int launch_tile_gp(GpIO<T> io, i64 batch, int *dInfo, cudaStream_t st, DeviceSta
     template int invgpu::launch_gj_tile<T, N, TR, TC, invgpu::PtrIO<T>, MINB>(invgpu::PtrIO<T>, int, invgpu::i64, int *, cudaStream_t, invgpu::DeviceState *);
 #define INVGPU_ONESWEEP_INSTANTIATE(T, N, TR, TC, STAGE, MINB) \
     template int invgpu::launch_onesweep<T, N, TR, TC, STAGE, MINB>(invgpu::StridedIO<T>, invgpu::i64, int *, cudaStream_t, invgpu::DeviceState *);
+#define INVGPU_GP_THREAD_INSTANTIATE(T, N, WARPS, MINB) \
+    template int invgpu::launch_gp_thread<T, N, WARPS, MINB>(invgpu::GpIO<T>, invgpu::i64, int *, cudaStream_t, invgpu::DeviceState *);
 #define INVGPU_THREAD_BULK_INSTANTIATE(T, N, WARPS, MINB) \
     template int invgpu::launch_spd_thread_bulk<T, N, WARPS, MINB>(invgpu::StridedIO<T>, invgpu::i64, int *, cudaStream_t, invgpu::DeviceState *);
 #define INVGPU_SPD8_TMA_INSTANTIATE(T, NBUF, MINB) \

@@ -174,6 +174,11 @@ static int fast_general(IO io, int n, i64 batch, int *dInfo, cudaStream_t st, De
             }
             INVGPU_SPD8_TMA_ALL(INVGPU_GJ8_TRY)
         }
+        // dense batches of order exactly 16 / 32: column-split lanes, matrix in registers
+#define INVGPU_GJC_TRY(TT, N, CL, WARPS, MINB)                                                       \
+        if (which == 0 && std::is_same<T, TT>::value && n == N && dense_aligned(io, N))                \
+            return launch_gj_colsplit<TT, N, CL, WARPS, MINB>(*reinterpret_cast<StridedIO<TT> *>(&io), batch, dInfo, st, ds);
+        INVGPU_GJC_ALL(INVGPU_GJC_TRY)
     }
     if (which == 0 && n > INVGPU_GJT_MIN_N(T)) { INVGPU_GJT_ALL(INVGPU_GJT_TRY) }
     INVGPU_GJ_ALL(INVGPU_GJ_TRY)
@@ -221,6 +226,8 @@ static int fast_padded(PadIO<T> io, int tier_n, i64 batch, int *dInfo, cudaStrea
     if (op == 0 && n == N && dtype_bytes == (int)sizeof(TT) && STAGES_ == 7) return TR * TC <= 32 ? "warp-tile" : "cta-tile";
 #define INVGPU_TILE_NAME_GP(TT, N, TR, TC, MINB) \
     if (op == 2 && n == N && dtype_bytes == (int)sizeof(TT)) return TR * TC <= 32 ? "warp-tile" : "cta-tile";
+#define INVGPU_GJC_NAME(TT, N, CL, WARPS, MINB) \
+    if (op == 1 && n == N && dtype_bytes == (int)sizeof(TT)) return "gj-colsplit";
 #define INVGPU_GJ8_NAME(TT, NBUF, MINB) \
     if (op == 1 && n == 8 && dtype_bytes == (int)sizeof(TT)) return "thread-tma";
 #define INVGPU_GJT_NAME(TT, N, TR, TC, MINB) \
@@ -244,6 +251,7 @@ static const char *fast_tier_name(int op, int n, int dtype_bytes) {
     INVGPU_GP_THREAD_ALL(INVGPU_GP_THREAD_NAME)
     INVGPU_SWEEP_GP_ALL(INVGPU_SWEEP_GP_NAME)
     INVGPU_SPD8_TMA_ALL(INVGPU_GJ8_NAME)
+    INVGPU_GJC_ALL(INVGPU_GJC_NAME)
     INVGPU_GJT_ALL(INVGPU_GJT_NAME)
     INVGPU_GJ_ALL(INVGPU_GJ_NAME)
     INVGPU_TILE_SPD_ALL(INVGPU_TILE_NAME)

@@ -252,4 +252,175 @@ gj_tile_kernel(IO io, int n, i64 batch, int *__restrict__ info) {
     }
 }
 
+// ==========================================================================================
+// General inverse for n = 16 / 32: COLUMN-SPLIT lanes, the whole matrix in registers, no shared-memory
+// broadcast.  L = N / CL consecutive lanes own CL consecutive columns each (all N rows: N x CL registers),
+// which makes Gauss-Jordan with implicit partial pivoting cheap on both sides:
+//   * the pivot column k lives in ONE lane with static row indices: the arg-max is a private scan, the
+//     multipliers reach the other lanes by N shuffles of a statically named register;
+//   * the pivot ROW p is needed by every lane only for its OWN columns -- a `switch` over the N row slots
+//     reads (and restarts) it, no exchange at all.
+// One uniform update  a_rc += z_r * y_c  (z_p = -1, y_c = -row_c / pivot, y_k = -1 / pivot) covers the four
+// cases of the in-place algorithm, as in gj_tile_kernel.  I/O: a lane's columns are contiguous in the
+// column-major input, so each lane moves them with one 1-D bulk copy into a padded slot; the permuted result
+// is scattered into the (dense) staging area of the matrix and leaves with one bulk store per matrix.
+// Column index k = CL * owner + j: the loop over `owner` is rolled, the CL step bodies are static.
+// ==========================================================================================
+template <typename T, int N, int CL, int WARPS>
+struct GjcGeo {
+    static constexpr int L = N / CL;                               // lanes per matrix
+    static constexpr int MPW = 32 / L;                             // matrices per warp
+    static constexpr int BLOCK = 32 * WARPS, MPB = MPW * WARPS;
+    static constexpr int COLS_BYTES = CL * N * (int)sizeof(T);     // one lane's columns
+    static constexpr int SLOT = COLS_BYTES + 16;                   // padded: consecutive lanes start one bank group further
+    static constexpr int MAT_BYTES = N * N * (int)sizeof(T);
+    static constexpr int EPC = 16 / (int)sizeof(T);
+    static constexpr int PERM_BYTES = 2 * N * (int)sizeof(int);    // rowOfCol, colOfRow per matrix
+    static constexpr size_t SMEM = (size_t)WARPS * 32 * SLOT + (size_t)MPB * PERM_BYTES + WARPS * 8 + 16;
+    static_assert(L >= 1 && L <= 32 && (L & (L - 1)) == 0 && N <= 32, "lanes per matrix: a power of two; the row mask is 32 bits");
+};
+
+template <typename T, int N, int CL, int J>
+__device__ __forceinline__ void gjc_step(T (&a)[N][CL], int lig, int gbase, int owner, unsigned &done, int &st, int *row_of_col, int *col_of_row) {
+    const int k = CL * owner + J;
+    // ---- pivot search: private to the owner lane
+    T best = T(-1), bval = T(0);
+    int brow = N;
+    if (lig == owner) {
+        #pragma unroll
+        for (int r = 0; r < N; ++r) {
+            const T av = dev_abs(a[r][J]);
+            if (!((done >> r) & 1u) && av > best) { best = av; bval = a[r][J]; brow = r; }
+        }
+    }
+    const int p = __shfl_sync(0xffffffffu, brow, gbase + owner);
+    const T piv = __shfl_sync(0xffffffffu, bval, gbase + owner);
+    if (st == 0 && !(dev_abs(piv) > T(0))) st = k + 1;
+    // ---- multipliers: column k from the owner lane, z_p := -1
+    T z[N];
+    #pragma unroll
+    for (int r = 0; r < N; ++r) {
+        const T f = __shfl_sync(0xffffffffu, a[r][J], gbase + owner);
+        z[r] = (r == p) ? T(-1) : f;
+    }
+    // ---- pivot row for this lane's own columns (run-time slot: switch), restarted; the owner restarts column k
+    T y[CL];
+    #pragma unroll
+    for (int c = 0; c < CL; ++c) y[c] = T(0);
+    #pragma unroll
+    for (int r = 0; r < N; ++r) {
+        if (r == p) {
+            #pragma unroll
+            for (int c = 0; c < CL; ++c) { y[c] = a[r][c]; a[r][c] = T(0); }
+        }
+    }
+    if (lig == owner) {
+        #pragma unroll
+        for (int r = 0; r < N; ++r) a[r][J] = T(0);
+        y[J] = T(1);
+        if (p < N) { row_of_col[k] = p; col_of_row[p] = k; }
+    }
+    if (p < N) done |= 1u << p;
+    // ---- a_rc += z_r * y_c,  y_c = -row_c / pivot
+    const T nrp = T(-1) / piv;
+    #pragma unroll
+    for (int c = 0; c < CL; ++c) y[c] *= nrp;
+    #pragma unroll
+    for (int r = 0; r < N; ++r)
+        #pragma unroll
+        for (int c = 0; c < CL; ++c) a[r][c] = fma(z[r], y[c], a[r][c]);
+}
+
+template <typename T, int N, int CL, int J>
+struct GjcSteps {
+    static __device__ __forceinline__ void run(T (&a)[N][CL], int lig, int gbase, int owner, unsigned &done, int &st, int *roc, int *cor) {
+        gjc_step<T, N, CL, J>(a, lig, gbase, owner, done, st, roc, cor);
+        if constexpr (J + 1 < CL) GjcSteps<T, N, CL, J + 1>::run(a, lig, gbase, owner, done, st, roc, cor);
+    }
+};
+
+template <typename T, int N, int CL, int WARPS, int MINB>
+__global__ void __launch_bounds__((GjcGeo<T, N, CL, WARPS>::BLOCK), MINB)
+gj_colsplit_kernel(const T *__restrict__ in, i64 in_stride, T *__restrict__ out, i64 out_stride, i64 batch, int *__restrict__ info) {
+    using G = GjcGeo<T, N, CL, WARPS>;
+    constexpr int L = G::L, EPC = G::EPC;
+    extern __shared__ __align__(16) unsigned char smem_raw_gc[];
+    const int warp = threadIdx.x >> 5, wl = threadIdx.x & 31;
+    const int lig = wl % L, gbase = wl - lig, mat = wl / L;        // lane in group, first lane of the group, matrix of the warp
+    unsigned char *wbase = smem_raw_gc + (size_t)warp * 32 * G::SLOT;
+    unsigned char *slot = wbase + (size_t)wl * G::SLOT;            // this lane's input columns
+    unsigned char *stage = wbase + (size_t)gbase * G::SLOT;        // dense N x N staging of the result (reuses the group's slots)
+    int *row_of_col = reinterpret_cast<int *>(smem_raw_gc + (size_t)WARPS * 32 * G::SLOT) + (size_t)(warp * G::MPW + mat) * 2 * N;
+    int *col_of_row = row_of_col + N;
+    unsigned long long *bar = reinterpret_cast<unsigned long long *>(
+        smem_raw_gc + (((size_t)WARPS * 32 * G::SLOT + (size_t)G::MPB * G::PERM_BYTES + 15) & ~(size_t)15)) + warp;
+    if (wl == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const i64 ntiles = (batch + G::MPW - 1) / G::MPW;
+    const i64 tstride = (i64)gridDim.x * WARPS;
+    i64 tile = (i64)blockIdx.x * WARPS + warp;
+    auto issue = [&](i64 t) {
+        const i64 m = t * G::MPW + mat;
+        const i64 left = batch - t * G::MPW;
+        if (wl == 0) mbar_expect_tx(bar, (unsigned)((left < G::MPW ? left : G::MPW) * G::MAT_BYTES));
+        __syncwarp();
+        if (m < batch) bulk_load_1d(slot, in + m * in_stride + (i64)lig * CL * N, G::COLS_BYTES, bar);
+    };
+    if (tile < ntiles) issue(tile);
+    unsigned phase = 0;
+    #pragma unroll 1
+    for (; tile < ntiles; tile += tstride) {
+        const i64 m = tile * G::MPW + mat;
+        const bool valid = m < batch;
+        mbar_wait(bar, phase);
+        phase ^= 1;
+
+        T a[N][CL];                                                // a[r][c] = A(r, CL * lig + c)
+        #pragma unroll
+        for (int c = 0; c < CL; ++c)
+            #pragma unroll
+            for (int r = 0; r < N; r += EPC) {
+                const T *p = reinterpret_cast<const T *>(slot + (c * N + r) * (int)sizeof(T));
+                #pragma unroll
+                for (int e = 0; e < EPC; ++e) a[r + e][c] = p[e];
+            }
+        unsigned done = 0;
+        int st = 0;
+        #pragma unroll 1
+        for (int owner = 0; owner < L; ++owner) GjcSteps<T, N, CL, 0>::run(a, lig, gbase, owner, done, st, row_of_col, col_of_row);
+        __syncwarp();                                              // permutation arrays visible; every lane is done with its slot
+
+        // ---- scatter M[r][c] = Ainv[colOfRow[r]][rowOfCol[c]] into the dense staging area (NaN if flagged)
+        T *sg = reinterpret_cast<T *>(stage);
+        if (st) {
+            #pragma unroll
+            for (int c = 0; c < CL; ++c)
+                #pragma unroll
+                for (int r = 0; r < N; ++r) sg[(CL * lig + c) * N + r] = dev_nan<T>();
+        } else {
+            int ocol[CL];
+            #pragma unroll
+            for (int c = 0; c < CL; ++c) ocol[c] = row_of_col[CL * lig + c];
+            #pragma unroll
+            for (int r = 0; r < N; ++r) {
+                const int orow = col_of_row[r];
+                #pragma unroll
+                for (int c = 0; c < CL; ++c) sg[ocol[c] * N + orow] = a[r][c];
+            }
+        }
+        if (valid && lig == 0 && info) info[m] = st;
+        fence_proxy_async();
+        __syncwarp();
+        if (valid && lig == 0) bulk_store_1d(out + m * out_stride, stage, G::MAT_BYTES);
+        asm volatile("cp.async.bulk.commit_group;\n\tcp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncwarp();                                              // every staging area has been read: slots reusable
+        if (tile + tstride < ntiles) issue(tile + tstride);
+    }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 }  // namespace invgpu

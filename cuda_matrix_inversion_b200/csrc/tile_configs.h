@@ -137,3 +137,8 @@
 #define INVGPU_GP_THREAD_F32(X) X(float, 8, 4, 4) X(float, 16, 2, 3)
 #define INVGPU_GP_THREAD_F64(X) X(double, 8, 4, 3)
 #define INVGPU_GP_THREAD_ALL(X) INVGPU_GP_THREAD_F32(X) INVGPU_GP_THREAD_F64(X)
+
+// general inverse, column-split lanes, matrix in registers (gj_colsplit_kernel):  X(T, N, CL, WARPS, MINB)
+#define INVGPU_GJC_F32(X) X(float, 16, 8, 4, 2) X(float, 32, 4, 4, 2)
+#define INVGPU_GJC_F64(X) X(double, 16, 4, 4, 2)
+#define INVGPU_GJC_ALL(X) INVGPU_GJC_F32(X) INVGPU_GJC_F64(X)

@@ -19,6 +19,9 @@ int launch_gj(IO io, int n, i64 batch, int *dInfo, cudaStream_t st, DeviceState 
 template <typename T, int N, int TR, int TC, typename IO, int MINB>
 int launch_gj_tile(IO io, int n, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds);
 
+template <typename T, int N, int CL, int WARPS, int MINB>
+int launch_gj_colsplit(StridedIO<T> io, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds);
+
 template <typename T, int N, int TR, int TC, bool STAGE, int MINB>
 int launch_onesweep(StridedIO<T> io, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds);
 
@@ -274,6 +277,18 @@ int launch_gj(IO io, int n, i64 batch, int *dInfo, cudaStream_t st, DeviceState 
     return (int)cudaGetLastError();
 }
 
+template <typename T, int N, int CL, int WARPS, int MINB>
+int launch_gj_colsplit(StridedIO<T> io, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds) {
+    using G = GjcGeo<T, N, CL, WARPS>;
+    auto kern = gj_colsplit_kernel<T, N, CL, WARPS, MINB>;
+    int grid = 0;
+    int rc = persistent_grid(kern, G::BLOCK, G::SMEM, (batch + G::MPB - 1) / G::MPB, ds, &grid);
+    if (rc) return rc;
+    kern<<<grid, G::BLOCK, G::SMEM, st>>>(io.in, io.in_stride, io.out, io.out_stride, batch, dInfo);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return (int)cudaGetLastError();
+}
+
 template <typename T, int N, int TR, int TC, typename IO, int MINB>
 int launch_gj_tile(IO io, int n, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds) {
     using G = GjtGeo<T, N, TR, TC>;
@@ -323,6 +338,8 @@ int launch_tile_gp(GpIO<T> io, i64 batch, int *dInfo, cudaStream_t st, DeviceSta
 #define INVGPU_GJ_INSTANTIATE(T, N, ROWS, MINB) \
     template int invgpu::launch_gj<T, N, ROWS, invgpu::StridedIO<T>, MINB>(invgpu::StridedIO<T>, int, invgpu::i64, int *, cudaStream_t, invgpu::DeviceState *); \
     template int invgpu::launch_gj<T, N, ROWS, invgpu::PtrIO<T>, MINB>(invgpu::PtrIO<T>, int, invgpu::i64, int *, cudaStream_t, invgpu::DeviceState *);
+#define INVGPU_GJC_INSTANTIATE(T, N, CL, WARPS, MINB) \
+    template int invgpu::launch_gj_colsplit<T, N, CL, WARPS, MINB>(invgpu::StridedIO<T>, invgpu::i64, int *, cudaStream_t, invgpu::DeviceState *);
 #define INVGPU_GJT_INSTANTIATE(T, N, TR, TC, MINB) \
     template int invgpu::launch_gj_tile<T, N, TR, TC, invgpu::StridedIO<T>, MINB>(invgpu::StridedIO<T>, int, invgpu::i64, int *, cudaStream_t, invgpu::DeviceState *); \
     template int invgpu::launch_gj_tile<T, N, TR, TC, invgpu::PtrIO<T>, MINB>(invgpu::PtrIO<T>, int, invgpu::i64, int *, cudaStream_t, invgpu::DeviceState *);

@@ -112,6 +112,40 @@ __global__ void k_mma_f64(float *out, float s) {
     out[blockIdx.x * blockDim.x + threadIdx.x] = (float)r;
 }
 
+__global__ void k_shfl(float *out, float s) {
+    float a[16];
+    for (int i = 0; i < 16; ++i) a[i] = threadIdx.x * 0.001f + i;
+    const int src = (threadIdx.x + 5) & 31;
+    for (int it = 0; it < ITERS; ++it) {
+        #pragma unroll
+        for (int i = 0; i < 16; ++i) a[i] = __shfl_sync(0xffffffffu, a[i], src);
+    }
+    float r = 0; for (int i = 0; i < 16; ++i) r += a[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = r;
+}
+// shuffles interleaved with FFMA2 (2 : 1), as in a shuffle-broadcast rank-1 update
+__global__ void k_shfl_ffma2(float *out, float s) {
+    float a[8];
+    unsigned long long acc[16], x;
+    for (int i = 0; i < 8; ++i) a[i] = threadIdx.x * 0.001f + i;
+    for (int i = 0; i < 16; ++i) { float lo = threadIdx.x + i, hi = lo + 1; asm("mov.b64 %0, {%1,%2};" : "=l"(acc[i]) : "f"(lo), "f"(hi)); }
+    asm("mov.b64 %0, {%1,%2};" : "=l"(x) : "f"(s), "f"(s));
+    const int src = (threadIdx.x + 5) & 31;
+    for (int it = 0; it < ITERS; ++it) {
+        #pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            a[i] = __shfl_sync(0xffffffffu, a[i], src);
+            unsigned long long y; asm("mov.b64 %0, {%1,%2};" : "=l"(y) : "f"(a[i]), "f"(a[i]));
+            asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[2 * i]) : "l"(x), "l"(y));
+            asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[2 * i + 1]) : "l"(x), "l"(y));
+        }
+    }
+    float r = 0;
+    for (int i = 0; i < 16; ++i) { float lo, hi; asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(acc[i])); r += lo + hi; }
+    for (int i = 0; i < 8; ++i) r += a[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = r;
+}
+
 template <typename K>
 static void run(const char *name, K kern, double ops_per_thread_iter, int threads, int blocks_per_sm) {
     int dev = 0, sms = 0; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -141,6 +175,8 @@ int main() {
         run("mma_tf32", k_mma_tf32, 8 * 16 * 8 * 8 / 32.0, 512, bps);   // FMAs per thread
         run("mma_bf16", k_mma_bf16, 8 * 16 * 8 * 16 / 32.0, 512, bps);
         run("mma_f64", k_mma_f64, 8 * 8 * 8 * 4 / 32.0, 512, bps);
+        run("shfl (lanes)", k_shfl, 16, 512, bps);          // ops = lane-shuffles: 32 per warp instruction
+        run("shfl+2ffma2", k_shfl_ffma2, 8, 512, bps);     // ops = lane-shuffles, two FFMA2 per shuffle alongside
     }
     return 0;
 }

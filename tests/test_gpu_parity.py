@@ -594,6 +594,56 @@ def test_full_size_gp_25k_128(api, torch):
     assert float((means[idx].double() - ref).abs().max()) <= 1e-4
 
 
+# --------------------------------------------------------------------------------------- ragged batches
+@pytest.mark.parametrize("batch", [1, 3, 31, 32, 33, 127, 129, 515])
+def test_ragged_batches_bulk_copy_kernels(api, batch):
+    """The thread-per-matrix / TMA / bulk-copy kernels move whole warp tiles; partial last tiles (and batches smaller
+    than one tile) must arm their mbarriers with the right byte counts and never touch memory beyond the batch:
+    guard bands around the outputs stay intact, every result matches the oracle."""
+    rng = np.random.default_rng(batch)
+    for n in (8, 16, 32):
+        r = rng.random((batch, n, n))
+        spd = (r + r.transpose(0, 2, 1) + n * np.eye(n)).astype(np.float32)
+        flat = orc.to_colmajor(spd)
+        got, info = api.spd_inverse_host(flat, n)
+        want, _ = orc.chol_inverse(flat, n)
+        assert not info.any()
+        assert np.abs(got - want).max() <= 1e-4 * np.abs(want).max(), ("spd", n, batch)
+        gen = (rng.random((batch, n, n)) - 0.5 + 0.5 * n * np.eye(n)).astype(np.float32)   # diagonally dominant: cond = O(1)
+        flat = orc.to_colmajor(gen)
+        got, info = api.general_inverse_host(flat, n)
+        want, _ = orc.gauss_jordan_inverse(flat, n)
+        assert not info.any()
+        assert np.abs(got - want).max() <= 1e-4 * np.abs(want).max(), ("general", n, batch)
+    for n in (8, 16):
+        g = gp_batch(n, batch, np.float32, seed=batch)
+        fl = {k: orc.to_colmajor(v) if v.ndim == 3 else v.reshape(-1) for k, v in g.items()}
+        means, var, info = api.gp_host(n, fl["a"], fl["b"], fl["c"], fl["d"], fl["e"])
+        om, _ = orc.gp_mean(n, fl["a"], fl["b"], fl["c"], fl["d"])
+        ov, _ = orc.gp_variance(n, fl["a"], fl["b"], fl["c"], fl["e"])
+        assert not info.any()
+        assert np.abs(means - om).max() <= 1e-4 and np.abs(var - ov).max() <= 1e-4, ("gp", n, batch)
+
+
+def test_device_outputs_have_intact_guard_bands(api, torch):
+    """Device flavour: outputs embedded in a larger buffer filled with a sentinel; nothing outside may change."""
+    for n, batch in ((8, 45), (16, 45), (32, 45), (32, 1)):
+        rng = np.random.default_rng(n + batch)
+        r = rng.random((batch, n, n))
+        spd = torch.from_numpy((r + r.transpose(0, 2, 1) + n * np.eye(n)).astype(np.float32)).cuda()
+        pad = 4096
+        buf = torch.full((pad + batch * n * n + pad,), 777.0, dtype=torch.float32, device="cuda")
+        out = buf[pad:pad + batch * n * n]
+        info = torch.zeros(batch, dtype=torch.int32, device="cuda")
+        st = torch.cuda.current_stream().cuda_stream
+        api.spd_inverse_device(spd.data_ptr(), out.data_ptr(), n, batch, np.float32, info.data_ptr(), st)
+        api.general_inverse_device(spd.data_ptr(), out.data_ptr(), n, batch, np.float32, info.data_ptr(), st)
+        torch.cuda.synchronize()
+        assert bool((buf[:pad] == 777.0).all()) and bool((buf[pad + batch * n * n:] == 777.0).all()), (n, batch)
+        want = torch.linalg.inv(spd.double().transpose(1, 2)).transpose(1, 2).float().reshape(-1)
+        assert float((out - want).abs().max()) <= 1e-4 * float(want.abs().max())
+
+
 # --------------------------------------------------------------------------------------- kernel variants
 _VARIANT_SNIPPET = r"""
 import sys, numpy as np

@@ -601,6 +601,21 @@ def test_ragged_batches_bulk_copy_kernels(api, batch):
     than one tile) must arm their mbarriers with the right byte counts and never touch memory beyond the batch:
     guard bands around the outputs stay intact, every result matches the oracle."""
     rng = np.random.default_rng(batch)
+    for n, dt in ((8, np.float64), (16, np.float64)):               # fp64: single-box TMA kernel, column-split GJ, GP thread kernel
+        r = rng.random((batch, n, n))
+        flat = orc.to_colmajor((r + r.transpose(0, 2, 1) + n * np.eye(n)).astype(dt))
+        got, info = api.spd_inverse_host(flat, n)
+        want, _ = orc.chol_inverse(flat, n)
+        assert not info.any() and np.abs(got - want).max() <= 1e-10 * np.abs(want).max(), ("spd f64", n, batch)
+        flat = orc.to_colmajor((rng.random((batch, n, n)) - 0.5 + 0.5 * n * np.eye(n)).astype(dt))
+        got, info = api.general_inverse_host(flat, n)
+        want, _ = orc.gauss_jordan_inverse(flat, n)
+        assert not info.any() and np.abs(got - want).max() <= 1e-10 * np.abs(want).max(), ("general f64", n, batch)
+        g = gp_batch(n, batch, dt, seed=batch + n)
+        fl = {k: orc.to_colmajor(v) if v.ndim == 3 else v.reshape(-1) for k, v in g.items()}
+        means, var, info = api.gp_host(n, fl["a"], fl["b"], fl["c"], fl["d"], fl["e"])
+        om, _ = orc.gp_mean(n, fl["a"], fl["b"], fl["c"], fl["d"])
+        assert not info.any() and np.abs(means - om).max() <= 1e-10, ("gp f64", n, batch)
     for n in (8, 16, 32):
         r = rng.random((batch, n, n))
         spd = (r + r.transpose(0, 2, 1) + n * np.eye(n)).astype(np.float32)

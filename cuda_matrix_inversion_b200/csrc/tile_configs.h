@@ -90,7 +90,8 @@
 // the same kernel with TMA tile I/O (sweep_spd_tma_kernel; columns of exactly 128 bytes):  X(V, T, N, TR, TC, UNROLL, MINB, DIRECT_OUT, INTERLEAVE)
 // Measured on B200 (2^19 matrices, fraction of the HBM roofline): direct global access 0.512 (sweep_spd_kernel,
 // INVGPU_SWEEP_VARIANT=9 skips the TMA kernels), TMA in + out 0.508 (6), TMA in with prefetch + direct stores 0.507 (7), TMA in + out with INTERLEAVED
-// lanes 0.577 (0, the default; direct stores with interleaved lanes: 0.448, 4 x 2 lanes interleaved: 0.456): the kernel is bound by shared-memory bandwidth, and with the global side on the TMA
+// lanes 0.577 (0, the default; direct stores with interleaved lanes: 0.448, 4 x 2 lanes interleaved: 0.456; FULL symmetric
+// storage -- pivot column alone as the broadcast vector, no row part, no mirrored stores, a third more FMAs: 0.271): the kernel is bound by shared-memory bandwidth, and with the global side on the TMA
 // unit the lane map can be chosen for the publish stores alone.
 #ifndef INVGPU_TMA_N32_MINB
 #define INVGPU_TMA_N32_MINB 3

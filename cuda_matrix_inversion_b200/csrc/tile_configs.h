@@ -81,6 +81,7 @@
 //   fp32 n = 32: 0.51 vs 0.44   64: 0.28 vs 0.25   128: 0.18 vs 0.165   fp64 64: 0.229 vs 0.232   128: 0.112 vs 0.116
 // BLK = 0 (no look-ahead: publish -> barrier -> update through one rolled body per range, half the code):
 //   fp32 n = 32: 0.38 (2x4 lanes), 0.43 (4x4 lanes) vs 0.51;  n = 64: 0.23 vs 0.28  -- the look-ahead is worth 25-35 %.
+// Occupancy (fp32, CTAs per SM 2 / 3 / 4): n = 64: 0.275 / 0.283 / 0.168 (spills), n = 128: 0.171 / 0.182 / 0.100 (spills).
 // n = 32 fp32 on 2 x 2 lanes (16 x 16 tiles, strictly-upper blocks pruned, 254 registers, 2 CTAs per SM): 0.47 vs 0.51.
 // The 2x2 block pivots halve barriers and dependency chains but double the live operand registers (x1, x2, y1, y2)
 // and the shared-memory bytes per step; the kernels are not chain-bound enough for that to pay.  Thread grids:

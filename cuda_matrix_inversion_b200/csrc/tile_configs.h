@@ -72,8 +72,8 @@
 #define INVGPU_SWEEP_F32(X)                                                                     \
     X(0, float, 16, 2, 2, false, 4, 1)                                                          \
     X(0, float, 32, 2, 4, false, 3, 1) X(1, float, 32, 4, 2, false, 3, 1) X(4, float, 32, 2, 4, false, 3, 2) \
-    X(0, float, 64, 8, 4, false, 3, 1) X(3, float, 64, 4, 8, false, 3, 1) X(4, float, 64, 8, 4, false, 3, 2) \
-    X(0, float, 128, 16, 8, false, 3, 1) X(3, float, 128, 8, 16, false, 3, 1) X(4, float, 128, 16, 8, false, 3, 2)
+    X(0, float, 64, 4, 4, false, 2, 1) X(3, float, 64, 8, 4, false, 3, 1) X(4, float, 64, 4, 4, false, 2, 2) \
+    X(0, float, 128, 8, 8, false, 2, 1) X(3, float, 128, 16, 8, false, 3, 1) X(4, float, 128, 8, 8, false, 2, 2)
 #define INVGPU_SWEEP_F64(X)                                                                     \
     X(0, double, 16, 2, 2, false, 2, 1) X(0, double, 32, 4, 4, false, 2, 1) X(0, double, 64, 8, 8, false, 4, 1) X(0, double, 128, 16, 16, false, 1, 1) \
     X(4, double, 64, 8, 8, false, 4, 2) X(4, double, 128, 16, 16, false, 1, 2)
@@ -81,7 +81,11 @@
 //   fp32 n = 32: 0.51 vs 0.44   64: 0.28 vs 0.25   128: 0.18 vs 0.165   fp64 64: 0.229 vs 0.232   128: 0.112 vs 0.116
 // BLK = 0 (no look-ahead: publish -> barrier -> update through one rolled body per range, half the code):
 //   fp32 n = 32: 0.38 (2x4 lanes), 0.43 (4x4 lanes) vs 0.51;  n = 64: 0.23 vs 0.28  -- the look-ahead is worth 25-35 %.
-// Occupancy (fp32, CTAs per SM 2 / 3 / 4): n = 64: 0.275 / 0.283 / 0.168 (spills), n = 128: 0.171 / 0.182 / 0.100 (spills).
+// Tile size (fp32): 16 x 16 tiles with the strictly-upper blocks never materialised (160 accumulator registers, 255 in all)
+// beat 8 x 16 tiles: n = 64 on 4 x 4 lanes 0.359 vs 0.284 (8 x 4 lanes), n = 128 on 8 x 8 threads 0.227 vs 0.182 (16 x 8):
+// 5 FMAs per broadcast operand word instead of 4 -- the kernels are bound by shared-memory bandwidth.  (n = 32 on 2 x 2
+// lanes does not gain: 0.47.)
+// Occupancy (fp32, 8 x 16 tiles, CTAs per SM 2 / 3 / 4): n = 64: 0.275 / 0.283 / 0.168 (spills), n = 128: 0.171 / 0.182 / 0.100 (spills).
 // n = 32 fp32 on 2 x 2 lanes (16 x 16 tiles, strictly-upper blocks pruned, 254 registers, 2 CTAs per SM): 0.47 vs 0.51.
 // The 2x2 block pivots halve barriers and dependency chains but double the live operand registers (x1, x2, y1, y2)
 // and the shared-memory bytes per step; the kernels are not chain-bound enough for that to pay.  Thread grids:
@@ -107,16 +111,17 @@
 // Measured on B200 against the three-phase tile kernels above (fraction of the HBM roofline, sweep vs tile):
 // fp32 n = 32: 0.45 vs 0.57, 64: 0.23 vs 0.39, 128: 0.118 vs 0.092; fp64 32/64/128: equal within 5 %.
 // Only the CTA tier gains (one barrier per pivot instead of the rolled potrf's per-pivot chain), so only
-// that one is dispatched (16 x 8 threads with 2x2 block pivots: 0.123; 8 x 16 scalar pivots: 0.118); the warp tiers stay on the fully unrolled tile kernels with exact static pruning.
-#define INVGPU_SWEEP_GP_F32(X) X(0, float, 128, 16, 8, false, 3, 2) X(3, float, 128, 8, 16, false, 3, 1)
+// that one is dispatched (8 x 8 threads with 16 x 16 tiles: 0.183, with 2x2 block pivots 0.177; 16 x 8 threads with 2x2 block
+// pivots: 0.123; 8 x 16 scalar pivots: 0.118; the sweep on 4 x 4 lanes at n = 64: 0.325 vs 0.386 for the tile kernel); the warp tiers stay on the fully unrolled tile kernels with exact static pruning.
+#define INVGPU_SWEEP_GP_F32(X) X(0, float, 128, 8, 8, false, 2, 1) X(3, float, 128, 16, 8, false, 3, 2)
 #define INVGPU_SWEEP_GP_F64(X)
 #define INVGPU_SWEEP_GP_ALL(X) INVGPU_SWEEP_GP_F32(X) INVGPU_SWEEP_GP_F64(X)
 
 // mixed-dimension batches on the sweep kernel with the padded IO policy:  X(T, N, TR, TC, MINB); tiers in ascending N
 // (intermediate tiers 24 / 48 / 96 / 192 on square grids: their strictly-upper 4x4 blocks are never materialised, so a
 //  12 x 12 tile costs 96 registers; they cut the (N / n)^3 padding waste of a tier from 3.0 to 1.7 on average)
-#define INVGPU_SWEEP_PAD_F32(X) X(float, 16, 2, 2, 4) X(float, 24, 2, 2, 3) X(float, 32, 2, 4, 3) X(float, 48, 4, 4, 3) X(float, 64, 8, 4, 3) \
-    X(float, 96, 8, 8, 4) X(float, 128, 16, 8, 3) X(float, 192, 16, 16, 1) X(float, 256, 16, 16, 1)
+#define INVGPU_SWEEP_PAD_F32(X) X(float, 16, 2, 2, 4) X(float, 24, 2, 2, 3) X(float, 32, 2, 4, 3) X(float, 48, 4, 4, 3) X(float, 64, 4, 4, 2) \
+    X(float, 96, 8, 8, 4) X(float, 128, 8, 8, 2) X(float, 192, 16, 16, 1) X(float, 256, 16, 16, 1)
 #define INVGPU_SWEEP_PAD_F64(X) X(double, 16, 2, 2, 2) X(double, 32, 4, 4, 2) X(double, 64, 8, 8, 4) X(double, 128, 16, 16, 1)
 #define INVGPU_SWEEP_PAD_ALL(X) INVGPU_SWEEP_PAD_F32(X) INVGPU_SWEEP_PAD_F64(X)
 

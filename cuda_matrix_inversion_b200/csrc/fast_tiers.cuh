@@ -159,10 +159,10 @@ template <typename T, typename TT> struct IOCast<PtrIO<T>, TT> { typedef PtrIO<T
 
 template <typename T, typename IO>
 static int fast_general(IO io, int n, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds) {
-    static int which = -1;                            // INVGPU_GJ_KERNEL=rowlane | generic: the older tiers (experiments)
+    static int which = -1;                            // INVGPU_GJ_KERNEL=rowlane | generic | colsplit: other tiers (experiments)
     if (which < 0) {
         const char *e = getenv("INVGPU_GJ_KERNEL");
-        which = (e && !strcmp(e, "rowlane")) ? 1 : (e && !strcmp(e, "generic")) ? 2 : 0;
+        which = (e && !strcmp(e, "rowlane")) ? 1 : (e && !strcmp(e, "generic")) ? 2 : (e && !strcmp(e, "colsplit")) ? 3 : 0;
     }
     if (which == 2) return INVGPU_NO_FAST_PATH;
     if constexpr (std::is_same<IO, StridedIO<T>>::value) {        // dense batches of order exactly 8: one thread per matrix + TMA
@@ -174,13 +174,14 @@ static int fast_general(IO io, int n, i64 batch, int *dInfo, cudaStream_t st, De
             }
             INVGPU_SPD8_TMA_ALL(INVGPU_GJ8_TRY)
         }
-        // dense batches of order exactly 16 / 32: column-split lanes, matrix in registers
+        // dense batches of order exactly 16 / 32: column-split lanes, matrix in registers (the default for fp64 only:
+        // at fp32 the lean lane = row kernel is faster, tile_configs.h)
 #define INVGPU_GJC_TRY(TT, N, CL, WARPS, MINB)                                                       \
-        if (which == 0 && std::is_same<T, TT>::value && n == N && dense_aligned(io, N))                \
+        if ((which == 3 || (which == 0 && INVGPU_GJC_DEFAULT(TT))) && std::is_same<T, TT>::value && n == N && dense_aligned(io, N)) \
             return launch_gj_colsplit<TT, N, CL, WARPS, MINB>(*reinterpret_cast<StridedIO<TT> *>(&io), batch, dInfo, st, ds);
         INVGPU_GJC_ALL(INVGPU_GJC_TRY)
     }
-    if (which == 0 && n > INVGPU_GJT_MIN_N(T)) { INVGPU_GJT_ALL(INVGPU_GJT_TRY) }
+    if ((which == 0 || which == 3) && n > INVGPU_GJT_MIN_N(T)) { INVGPU_GJT_ALL(INVGPU_GJT_TRY) }
     INVGPU_GJ_ALL(INVGPU_GJ_TRY)
     return INVGPU_NO_FAST_PATH;
 }
@@ -227,7 +228,7 @@ static int fast_padded(PadIO<T> io, int tier_n, i64 batch, int *dInfo, cudaStrea
 #define INVGPU_TILE_NAME_GP(TT, N, TR, TC, MINB) \
     if (op == 2 && n == N && dtype_bytes == (int)sizeof(TT)) return TR * TC <= 32 ? "warp-tile" : "cta-tile";
 #define INVGPU_GJC_NAME(TT, N, CL, WARPS, MINB) \
-    if (op == 1 && n == N && dtype_bytes == (int)sizeof(TT)) return "gj-colsplit";
+    if (op == 1 && n == N && dtype_bytes == (int)sizeof(TT) && INVGPU_GJC_DEFAULT(TT)) return "gj-colsplit";
 #define INVGPU_GJ8_NAME(TT, NBUF, MINB) \
     if (op == 1 && n == 8 && dtype_bytes == (int)sizeof(TT)) return "thread-tma";
 #define INVGPU_GJT_NAME(TT, N, TR, TC, MINB) \

@@ -81,6 +81,142 @@ gj_rowlane_kernel(IO io, int n, i64 batch, int *__restrict__ info) {
         #pragma unroll
         for (int q = 0; q < ROWS; ++q) { mystep[q] = 0; pivoted[q] = false; }
 
+        if constexpr (ROWS <= 2) {
+            // ---- lean form (one or two rows per lane): ~70-95 issue slots per matrix and pivot instead of ~220.
+            //  * fp32 pivot search: |a| as an unsigned key -> one REDUX max + one ballot per row slot (first maximum
+            //    wins ties, like isamax);
+            //  * the pivot lane publishes its RAW row; the uniform update  a_ic += z_i * row_c  with  z_i = -a_ik / piv
+            //    needs no select per element (z_p = -1 makes the pivot row's registers exact zeros; a second in-place
+            //    FMA with the multiplier 1/piv in the pivot row and 0 elsewhere turns it into row / piv), z is the new column k;
+            //  * fp32 updates are packed (FFMA2: two columns per issue slot);
+            //  * two rows per lane halve the shared-memory wavefronts per matrix (a broadcast LDS costs 4 bytes per
+            //    lane and clock whatever the address pattern: with one row per lane that is one word per FMA).
+            const unsigned gmask = (L == 32) ? 0xffffffffu : (((1u << (L & 31)) - 1u) << (lane - l));
+            #pragma unroll
+            for (int k = 0; k < N; ++k) {
+                T *pr_line = line + (k & 1) * N;
+                int pl, pq = 0;                                    // absolute lane and row slot of the pivot row
+                bool none;
+                if constexpr (sizeof(T) == 4) {
+                    unsigned key[ROWS], mykey = 0u;
+                    #pragma unroll
+                    for (int q = 0; q < ROWS; ++q) {
+                        const float v = fabsf((float)a[q][k]);
+                        key[q] = (!pivoted[q] && v == v) ? __float_as_uint(v) : 0u;
+                        mykey = max(mykey, key[q]);
+                    }
+                    const unsigned mx = __reduce_max_sync(gmask, mykey);
+                    unsigned cand = __ballot_sync(0xffffffffu, !pivoted[0] && key[0] == mx) & gmask;
+                    #pragma unroll
+                    for (int q = 1; q < ROWS; ++q) {
+                        const unsigned cq = __ballot_sync(0xffffffffu, !pivoted[q] && key[q] == mx) & gmask;
+                        if (cand == 0u) { cand = cq; pq = q; }
+                    }
+                    pl = __ffs((int)cand) - 1;
+                    none = mx == 0u;
+                } else {
+                    T best = T(-1);
+                    int prow = N;
+                    #pragma unroll
+                    for (int q = 0; q < ROWS; ++q) {
+                        const T v = dev_abs(a[q][k]);
+                        if (!pivoted[q] && v > best) { best = v; prow = l + L * q; }     // NaN never wins
+                    }
+                    #pragma unroll
+                    for (int o = L / 2; o > 0; o >>= 1) {
+                        const T ob = __shfl_xor_sync(0xffffffffu, best, o);
+                        const int orow = __shfl_xor_sync(0xffffffffu, prow, o);
+                        if (ob > best || (ob == best && orow < prow)) { best = ob; prow = orow; }
+                    }
+                    none = !(best > T(0));
+                    // only NaNs left: take the first row that has not been a pivot (warp-wide ballots: unconditional)
+                    unsigned cand = __ballot_sync(0xffffffffu, !pivoted[0]) & gmask;
+                    int cq_slot = 0;
+                    #pragma unroll
+                    for (int q = 1; q < ROWS; ++q) {
+                        const unsigned cq = __ballot_sync(0xffffffffu, !pivoted[q]) & gmask;
+                        if (cand == 0u) { cand = cq; cq_slot = q; }
+                    }
+                    if (prow >= N) prow = (__ffs((int)cand) - 1 - (lane - l)) + L * cq_slot;
+                    pl = (lane - l) + prow % L;
+                    pq = (prow / L) % ROWS;
+                }
+                if (st == 0 && none) st = k + 1;                   // uniform inside the group
+                T mine_k = a[0][k];
+                #pragma unroll
+                for (int q = 1; q < ROWS; ++q) mine_k = (pq == q) ? a[q][k] : mine_k;
+                const T pivv = __shfl_sync(0xffffffffu, mine_k, pl);
+                T r;
+                if constexpr (sizeof(T) == 4) asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(pivv));   // 1 ulp, no slow path
+                else r = T(1) / pivv;
+                const bool isl = lane == pl;
+                bool isp[ROWS];
+                T z[ROWS];
+                #pragma unroll
+                for (int q = 0; q < ROWS; ++q) {
+                    isp[q] = isl && pq == q;
+                    z[q] = isp[q] ? T(-1) : -a[q][k] * r;          // z_p = -1: a - a = 0 exactly, then r * row
+                }
+                T w[ROWS];                                         // second multiplier: r for the pivot row, 0 elsewhere
+                #pragma unroll
+                for (int q = 0; q < ROWS; ++q) w[q] = isp[q] ? r : T(0);
+                #pragma unroll
+                for (int q = 0; q < ROWS; ++q) {
+                    if (isp[q]) {                                  // one branch per row slot: static register names, no selects
+                        #pragma unroll
+                        for (int c4 = 0; c4 < N; c4 += 4) {
+                            if constexpr (sizeof(T) == 4) {
+                                // 64-bit stores straight from the FFMA2 register pairs (a merged 128-bit store costs four staging moves)
+                                const unsigned sa = (unsigned)__cvta_generic_to_shared(pr_line + c4);
+                                asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(sa), "f"((float)a[q][c4]), "f"((float)a[q][c4 + 1]) : "memory");
+                                asm volatile("st.shared.v2.f32 [%0+8], {%1, %2};" ::"r"(sa), "f"((float)a[q][c4 + 2]), "f"((float)a[q][c4 + 3]) : "memory");
+                            } else {
+                                *reinterpret_cast<double2 *>(pr_line + c4) = make_double2((double)a[q][c4], (double)a[q][c4 + 1]);
+                                *reinterpret_cast<double2 *>(pr_line + c4 + 2) = make_double2((double)a[q][c4 + 2], (double)a[q][c4 + 3]);
+                            }
+                        }
+                        piv[k] = l + L * q;
+                        pivoted[q] = true;
+                        mystep[q] = k;
+                    }
+                }
+                __syncwarp();
+                // a += z * row (exact zero in the pivot row), then a += w * row (row / piv in the pivot row, a + 0 elsewhere):
+                // both in place and select-free
+                #pragma unroll
+                for (int c4 = 0; c4 < N; c4 += 4) {
+                    if constexpr (sizeof(T) == 4) {
+                        const float4 v = *reinterpret_cast<const float4 *>(pr_line + c4);
+                        #pragma unroll
+                        for (int q = 0; q < ROWS; ++q) {
+                            const float2 z2 = make_float2((float)z[q], (float)z[q]), w2 = make_float2((float)w[q], (float)w[q]);
+                            float2 lo = make_float2((float)a[q][c4], (float)a[q][c4 + 1]), hi = make_float2((float)a[q][c4 + 2], (float)a[q][c4 + 3]);
+                            lo = __ffma2_rn(z2, make_float2(v.x, v.y), lo);
+                            hi = __ffma2_rn(z2, make_float2(v.z, v.w), hi);
+                            lo = __ffma2_rn(w2, make_float2(v.x, v.y), lo);
+                            hi = __ffma2_rn(w2, make_float2(v.z, v.w), hi);
+                            a[q][c4] = lo.x; a[q][c4 + 1] = lo.y; a[q][c4 + 2] = hi.x; a[q][c4 + 3] = hi.y;
+                        }
+                    } else {
+                        const double2 u = *reinterpret_cast<const double2 *>(pr_line + c4);
+                        const double2 v = *reinterpret_cast<const double2 *>(pr_line + c4 + 2);
+                        #pragma unroll
+                        for (int q = 0; q < ROWS; ++q) {
+                            if (isp[q]) {
+                                a[q][c4] = r * (T)u.x; a[q][c4 + 1] = r * (T)u.y; a[q][c4 + 2] = r * (T)v.x; a[q][c4 + 3] = r * (T)v.y;
+                            } else {
+                                a[q][c4] = fma(z[q], (T)u.x, a[q][c4]);
+                                a[q][c4 + 1] = fma(z[q], (T)u.y, a[q][c4 + 1]);
+                                a[q][c4 + 2] = fma(z[q], (T)v.x, a[q][c4 + 2]);
+                                a[q][c4 + 3] = fma(z[q], (T)v.y, a[q][c4 + 3]);
+                            }
+                        }
+                    }
+                }
+                #pragma unroll
+                for (int q = 0; q < ROWS; ++q) a[q][k] = isp[q] ? r : z[q];
+            }
+        } else {
         #pragma unroll
         for (int k = 0; k < N; ++k) {
             T *pr_line = line + (k & 1) * N;
@@ -159,6 +295,7 @@ gj_rowlane_kernel(IO io, int n, i64 batch, int *__restrict__ info) {
                     }
                 }
             }
+        }
         }
         __syncwarp();
 

@@ -48,7 +48,22 @@
 #define INVGPU_TILE_GP_ALL(X) INVGPU_TILE_GP_F32(X) INVGPU_TILE_GP_F64(X)
 
 // general inverse, lane = row Gauss-Jordan (gj_kernels.cuh):  X(T, N, ROWS, MINB); N = padded order
-#define INVGPU_GJ_F32(X) X(float, 8, 1, 4) X(float, 16, 1, 4) X(float, 32, 1, 4)
+// Measured on B200 (fp32, dense, fraction of the HBM roofline; ROWS x CTAs per SM):
+//   n = 16: 1 x 4: 0.203, 1 x 6: 0.226, 2 x 4: 0.238, 2 x 6: 0.255 (default)      column-split lanes (INVGPU_GJC): 0.227
+//   n = 32: 1 x 4: 0.147, 1 x 6: 0.161 (default), 2 x 4: 0.154, 2 x 5: 0.134 (spills)   column-split lanes: 0.122
+#ifndef INVGPU_GJ32_MINB
+#define INVGPU_GJ32_MINB 6
+#endif
+#ifndef INVGPU_GJ16_MINB
+#define INVGPU_GJ16_MINB 6
+#endif
+#ifndef INVGPU_GJ32_ROWS
+#define INVGPU_GJ32_ROWS 1
+#endif
+#ifndef INVGPU_GJ16_ROWS
+#define INVGPU_GJ16_ROWS 2
+#endif
+#define INVGPU_GJ_F32(X) X(float, 8, 1, 4) X(float, 16, INVGPU_GJ16_ROWS, INVGPU_GJ16_MINB) X(float, 32, INVGPU_GJ32_ROWS, INVGPU_GJ32_MINB)
 #define INVGPU_GJ_F64(X) X(double, 8, 1, 4) X(double, 16, 1, 4) X(double, 32, 1, 3)
 #define INVGPU_GJ_ALL(X) INVGPU_GJ_F32(X) INVGPU_GJ_F64(X)
 
@@ -151,3 +166,4 @@
 #define INVGPU_GJC_F32(X) X(float, 16, 8, 4, 2) X(float, 32, 4, 4, 2)
 #define INVGPU_GJC_F64(X) X(double, 16, 4, 4, 2)
 #define INVGPU_GJC_ALL(X) INVGPU_GJC_F32(X) INVGPU_GJC_F64(X)
+#define INVGPU_GJC_DEFAULT(TT) (sizeof(TT) == 8)     // fp32: INVGPU_GJ_KERNEL=colsplit only (0.227 / 0.122 vs 0.255 / 0.161 for the lean lane = row kernel)

@@ -702,3 +702,46 @@ def test_sweep_kernel_variants(variant, n):
         assert "sweep_spd_tma_kernel" in p.stderr      # the TMA kernel really ran (no silent fallback)
     if variant == 9:
         assert "sweep_spd_tma_kernel" not in p.stderr  # the direct-access kernel
+
+
+_GJ_VARIANT_SNIPPET = r"""
+import sys, numpy as np
+sys.path.insert(0, {root!r})
+import oracle as orc
+from cuda_matrix_inversion_b200 import api
+n, batch, dt = {n}, {batch}, np.{dtype}
+rng = np.random.default_rng(7)
+a = (rng.random((batch, n, n)) - 0.5 + n * 0.25 * np.eye(n)).astype(dt)
+a[2, :, n // 2] = 0.0                                # zero column: info n/2 + 1
+a[5] = 0.0                                           # zero matrix: info 1
+a[batch - 1, :, n - 1] = np.nan                      # NaN column in the last (partial) warp tile: info n
+flat = orc.to_colmajor(a)
+got, info = api.general_inverse_host(flat, n)
+want, oinfo = orc.gauss_jordan_inverse(flat, n)
+assert (info == oinfo).all(), (info[info != oinfo], oinfo[info != oinfo])
+assert info[2] == n // 2 + 1 and info[5] == 1 and info[batch - 1] == n and (info != 0).sum() == 3
+good = info == 0
+g, w = orc.from_colmajor(got, n), orc.from_colmajor(want, n)
+err = np.abs(g[good] - w[good]).max() / np.abs(w[good]).max()
+assert err <= {tol}, err
+assert np.isnan(g[~good]).all()
+print("variant ok", err)
+"""
+
+
+@pytest.mark.parametrize("kernel,n,dtype", [("colsplit", 16, "float32"), ("colsplit", 32, "float32"), ("rowlane", 16, "float64"),
+                                            ("rowlane", 32, "float64"), ("rowlane", 8, "float32"), ("rowlane", 24, "float32"),
+                                            ("generic", 32, "float32")])
+def test_general_kernel_variants(kernel, n, dtype):
+    """The general-inverse tiers that are not the default for a shape (INVGPU_GJ_KERNEL = colsplit: column-split lanes
+    at fp32, rowlane: lane = row at fp64 / n = 8 / padded orders, generic: shared-memory tier) keep their parity tests:
+    one child process each, oracle parity, sgetrf flags (zero column, zero matrix, NaN column), ragged tail."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, INVGPU_GJ_KERNEL=kernel)
+    tol = 1e-4 if dtype == "float32" else 1e-10
+    p = subprocess.run([sys.executable, "-c", _GJ_VARIANT_SNIPPET.format(root=root, n=n, batch=1027, dtype=dtype, tol=tol)],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert "variant ok" in p.stdout

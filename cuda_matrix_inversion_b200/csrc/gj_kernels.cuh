@@ -64,14 +64,22 @@ gj_rowlane_kernel(IO io, int n, i64 batch, int *__restrict__ info) {
 
         // a[q][c] = A(row l + L q, column c); identity padding outside n
         T a[ROWS][N];
-        #pragma unroll
-        for (int q = 0; q < ROWS; ++q) {
-            const int row = l + L * q;
+        if (n == N) {                                              // exact order: compile-time offsets, no padding predicates
             #pragma unroll
-            for (int c = 0; c < N; ++c) {
-                T v = (row == c) ? T(1) : T(0);
-                if (row < n && c < n) v = __ldcs(src + (size_t)c * n + row);
-                a[q][c] = v;
+            for (int q = 0; q < ROWS; ++q) {
+                #pragma unroll
+                for (int c = 0; c < N; ++c) a[q][c] = __ldcs(src + c * N + l + L * q);
+            }
+        } else {
+            #pragma unroll
+            for (int q = 0; q < ROWS; ++q) {
+                const int row = l + L * q;
+                #pragma unroll
+                for (int c = 0; c < N; ++c) {
+                    T v = (row == c) ? T(1) : T(0);
+                    if (row < n && c < n) v = __ldcs(src + (size_t)c * n + row);
+                    a[q][c] = v;
+                }
             }
         }
 
@@ -303,6 +311,14 @@ gj_rowlane_kernel(IO io, int n, i64 batch, int *__restrict__ info) {
             if (l == 0 && info) info[m] = (st > n) ? 0 : st;       // a "singular" padded column cannot happen; guard anyway
             T *__restrict__ dst = io.dst(m);
             const bool bad = st != 0 && st <= n;
+            if (n == N && !bad) {                                  // the common case: 32-bit offsets, no bounds predicates
+                #pragma unroll
+                for (int c = 0; c < N; ++c) {
+                    const int ocol = piv[c] * N;
+                    #pragma unroll
+                    for (int q = 0; q < ROWS; ++q) __stcs(dst + ocol + mystep[q], a[q][c]);
+                }
+            } else
             #pragma unroll
             for (int c = 0; c < N; ++c) {
                 const int ocol = piv[c];                           // pi(c): broadcast read

@@ -51,6 +51,7 @@
 // Measured on B200 (fp32, dense, fraction of the HBM roofline; ROWS x CTAs per SM):
 //   n = 16: 1 x 4: 0.203, 1 x 6: 0.226, 2 x 4: 0.238, 2 x 6: 0.255 (default)      column-split lanes (INVGPU_GJC): 0.227
 //   n = 32: 1 x 4: 0.147, 1 x 6: 0.161 (default), 2 x 4: 0.154, 2 x 5: 0.134 (spills)   column-split lanes: 0.122
+// (before the exact-order load / store path; with it the defaults reach 0.289 at n = 16 and 0.203 at n = 32)
 #ifndef INVGPU_GJ32_MINB
 #define INVGPU_GJ32_MINB 6
 #endif

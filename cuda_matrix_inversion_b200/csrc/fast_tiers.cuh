@@ -12,8 +12,9 @@
 
 #define INVGPU_NO_FAST_PATH (-1000)
 // orders up to this bound stay on the lane = row kernel (gj_kernels.cuh), measured faster there on B200:
-// fp32 n = 16: 0.177 vs 0.147 of the HBM roofline, 32: 0.101 vs 0.074; fp64 32: 0.120 vs 0.138 (tile wins)
-#define INVGPU_GJT_MIN_N(T) (sizeof(T) == 4 ? 32 : 16)
+// fp32 n = 16: 0.289 vs 0.147 of the HBM roofline, 32: 0.203 vs 0.074; fp64 32: 0.159 vs 0.124 (the tile kernel won
+// against the first lane = row kernel, 0.138 vs 0.120, and loses against the lean one)
+#define INVGPU_GJT_MIN_N(T) 32
 #ifndef INVGPU_SWEEP_MIN_N
 #define INVGPU_SWEEP_MIN_N 16
 #endif
@@ -159,10 +160,10 @@ template <typename T, typename TT> struct IOCast<PtrIO<T>, TT> { typedef PtrIO<T
 
 template <typename T, typename IO>
 static int fast_general(IO io, int n, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds) {
-    static int which = -1;                            // INVGPU_GJ_KERNEL=rowlane | generic | colsplit: other tiers (experiments)
+    static int which = -1;                            // INVGPU_GJ_KERNEL=rowlane | generic | colsplit | tile: other tiers (experiments)
     if (which < 0) {
         const char *e = getenv("INVGPU_GJ_KERNEL");
-        which = (e && !strcmp(e, "rowlane")) ? 1 : (e && !strcmp(e, "generic")) ? 2 : (e && !strcmp(e, "colsplit")) ? 3 : 0;
+        which = (e && !strcmp(e, "rowlane")) ? 1 : (e && !strcmp(e, "generic")) ? 2 : (e && !strcmp(e, "colsplit")) ? 3 : (e && !strcmp(e, "tile")) ? 4 : 0;
     }
     if (which == 2) return INVGPU_NO_FAST_PATH;
     if constexpr (std::is_same<IO, StridedIO<T>>::value) {        // dense batches of order exactly 8: one thread per matrix + TMA
@@ -174,14 +175,14 @@ static int fast_general(IO io, int n, i64 batch, int *dInfo, cudaStream_t st, De
             }
             INVGPU_SPD8_TMA_ALL(INVGPU_GJ8_TRY)
         }
-        // dense batches of order exactly 16 / 32: column-split lanes, matrix in registers (the default for fp64 only:
-        // at fp32 the lean lane = row kernel is faster, tile_configs.h)
+        // dense batches of order exactly 16 / 32: column-split lanes, matrix in registers (INVGPU_GJ_KERNEL=colsplit only:
+        // the lean lane = row kernel is faster, tile_configs.h)
 #define INVGPU_GJC_TRY(TT, N, CL, WARPS, MINB)                                                       \
         if ((which == 3 || (which == 0 && INVGPU_GJC_DEFAULT(TT))) && std::is_same<T, TT>::value && n == N && dense_aligned(io, N)) \
             return launch_gj_colsplit<TT, N, CL, WARPS, MINB>(*reinterpret_cast<StridedIO<TT> *>(&io), batch, dInfo, st, ds);
         INVGPU_GJC_ALL(INVGPU_GJC_TRY)
     }
-    if ((which == 0 || which == 3) && n > INVGPU_GJT_MIN_N(T)) { INVGPU_GJT_ALL(INVGPU_GJT_TRY) }
+    if (((which == 0 || which == 3) && n > INVGPU_GJT_MIN_N(T)) || (which == 4 && n > 16)) { INVGPU_GJT_ALL(INVGPU_GJT_TRY) }
     INVGPU_GJ_ALL(INVGPU_GJ_TRY)
     return INVGPU_NO_FAST_PATH;
 }

@@ -52,6 +52,7 @@
 //   n = 16: 1 x 4: 0.203, 1 x 6: 0.226, 2 x 4: 0.238, 2 x 6: 0.255 (default)      column-split lanes (INVGPU_GJC): 0.227
 //   n = 32: 1 x 4: 0.147, 1 x 6: 0.161 (default), 2 x 4: 0.154, 2 x 5: 0.134 (spills)   column-split lanes: 0.122
 // (before the exact-order load / store path; with it the defaults reach 0.289 at n = 16 and 0.203 at n = 32)
+// fp64: n = 16: 1 x 4: 0.284, 2 x 4: 0.311 (default; column-split lanes 0.245); n = 32: 1 x 3: 0.151, 1 x 4: 0.159 (default; 4 x 4 tile kernel 0.124)
 #ifndef INVGPU_GJ32_MINB
 #define INVGPU_GJ32_MINB 6
 #endif
@@ -65,7 +66,13 @@
 #define INVGPU_GJ16_ROWS 2
 #endif
 #define INVGPU_GJ_F32(X) X(float, 8, 1, 4) X(float, 16, INVGPU_GJ16_ROWS, INVGPU_GJ16_MINB) X(float, 32, INVGPU_GJ32_ROWS, INVGPU_GJ32_MINB)
-#define INVGPU_GJ_F64(X) X(double, 8, 1, 4) X(double, 16, 1, 4) X(double, 32, 1, 3)
+#ifndef INVGPU_GJ16_ROWS_F64
+#define INVGPU_GJ16_ROWS_F64 2
+#endif
+#ifndef INVGPU_GJ32_MINB_F64
+#define INVGPU_GJ32_MINB_F64 4
+#endif
+#define INVGPU_GJ_F64(X) X(double, 8, 1, 4) X(double, 16, INVGPU_GJ16_ROWS_F64, 4) X(double, 32, 1, INVGPU_GJ32_MINB_F64)
 #define INVGPU_GJ_ALL(X) INVGPU_GJ_F32(X) INVGPU_GJ_F64(X)
 
 // SPD inverse, one-sweep Cholesky (onesweep_kernels.cuh), warp tiers:  X(T, N, TR, TC, STAGE, MINB)
@@ -167,4 +174,4 @@
 #define INVGPU_GJC_F32(X) X(float, 16, 8, 4, 2) X(float, 32, 4, 4, 2)
 #define INVGPU_GJC_F64(X) X(double, 16, 4, 4, 2)
 #define INVGPU_GJC_ALL(X) INVGPU_GJC_F32(X) INVGPU_GJC_F64(X)
-#define INVGPU_GJC_DEFAULT(TT) (sizeof(TT) == 8)     // fp32: INVGPU_GJ_KERNEL=colsplit only (0.227 / 0.122 vs 0.255 / 0.161 for the lean lane = row kernel)
+#define INVGPU_GJC_DEFAULT(TT) false                  // INVGPU_GJ_KERNEL=colsplit only: fp32 0.227 / 0.122 vs 0.289 / 0.203 for the lean lane = row kernel, fp64 n = 16 0.245 vs 0.311

@@ -731,10 +731,10 @@ print("variant ok", err)
 
 @pytest.mark.parametrize("kernel,n,dtype", [("colsplit", 16, "float32"), ("colsplit", 32, "float32"), ("rowlane", 16, "float64"),
                                             ("rowlane", 32, "float64"), ("rowlane", 8, "float32"), ("rowlane", 24, "float32"),
-                                            ("generic", 32, "float32")])
+                                            ("generic", 32, "float32"), ("colsplit", 16, "float64"), ("tile", 32, "float64"), ("tile", 24, "float64")])
 def test_general_kernel_variants(kernel, n, dtype):
     """The general-inverse tiers that are not the default for a shape (INVGPU_GJ_KERNEL = colsplit: column-split lanes
-    at fp32, rowlane: lane = row at fp64 / n = 8 / padded orders, generic: shared-memory tier) keep their parity tests:
+    rowlane: lane = row also at n = 8, tile: the 2-D tile kernel also at 17 <= n <= 32, generic: shared-memory tier) keep their parity tests:
     one child process each, oracle parity, sgetrf flags (zero column, zero matrix, NaN column), ragged tail."""
     import subprocess
     import sys

@@ -68,6 +68,7 @@ class ClockSampler:
         self.index = index
         self.proc = None
         self.lines = []
+        self.first = 0
 
     def start(self):
         try:
@@ -83,10 +84,16 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def mark(self):
+        """Samples taken before this point (warm-up) are dropped."""
+        self.first = len(self.lines)
+
+    def count_since_mark(self):
+        return len(self.lines) - self.first if self.proc else 1 << 30
+
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -94,7 +101,7 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ln in self.lines[self.first:]:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -288,12 +295,13 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()                      # before the warm-up: nvidia-smi needs ~0.2 s before its first sample
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    sampler.mark()
     launches0 = api.launch_count()
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     barrier()
@@ -305,6 +313,13 @@ def run_ours(args):
     per_step = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
     total_ms = evs[0].elapsed_time(evs[-1])
     launches = api.launch_count() - launches0
+    if rank == 0:
+        # the timed region is tens of milliseconds, nvidia-smi samples every 100 ms: keep the same kernel running
+        # (untimed) until a few samples under this load exist
+        t_end = time.time() + 1.0
+        while sampler.count_since_mark() < 4 and time.time() < t_end:
+            step()
+            torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
     assert int(info.abs().max()) == 0
     t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)

@@ -14,7 +14,8 @@
 // orders up to this bound stay on the lane = row kernel (gj_kernels.cuh), measured faster there on B200:
 // fp32 n = 16: 0.289 vs 0.147 of the HBM roofline, 32: 0.203 vs 0.074; fp64 32: 0.159 vs 0.124 (the tile kernel won
 // against the first lane = row kernel, 0.138 vs 0.120, and loses against the lean one)
-#define INVGPU_GJT_MIN_N(T) 32
+// fp32 n = 64: 0.108 (two rows per lane) vs 0.068
+#define INVGPU_GJT_MIN_N(T) (sizeof(T) == 4 ? 64 : 32)
 #ifndef INVGPU_SWEEP_MIN_N
 #define INVGPU_SWEEP_MIN_N 16
 #endif

@@ -52,6 +52,7 @@
 //   n = 16: 1 x 4: 0.203, 1 x 6: 0.226, 2 x 4: 0.238, 2 x 6: 0.255 (default)      column-split lanes (INVGPU_GJC): 0.227
 //   n = 32: 1 x 4: 0.147, 1 x 6: 0.161 (default), 2 x 4: 0.154, 2 x 5: 0.134 (spills)   column-split lanes: 0.122
 // (before the exact-order load / store path; with it the defaults reach 0.289 at n = 16 and 0.203 at n = 32)
+// 8 CTAs per SM (64 registers, spills): n = 16: 0.252, n = 32: 0.206 -- not worth it
 // fp64: n = 16: 1 x 4: 0.284, 2 x 4: 0.311 (default; column-split lanes 0.245); n = 32: 1 x 3: 0.151, 1 x 4: 0.159 (default; 4 x 4 tile kernel 0.124)
 #ifndef INVGPU_GJ32_MINB
 #define INVGPU_GJ32_MINB 6

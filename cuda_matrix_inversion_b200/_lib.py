@@ -32,6 +32,8 @@ def _load() -> C.CDLL:
         "invgpu_host_alloc": (_vp, [C.c_ulonglong]),
         "invgpu_host_free": (None, [_vp]),
         "invgpu_release_workspace": (None, []),
+        "invgpu_xfer_roundtrip_host": (_int, [_vp, _vp, C.c_ulonglong, _i64]),
+        "invgpu_device_numa_node": (_int, [_int]),
     }
     for sfx in ("f32", "f64"):
         sig[f"invgpu_spd_inverse_{sfx}"] = (_int, [_vp, _vp, _int, _i64, _vp, _vp])

@@ -4,6 +4,7 @@
 #include <errno.h>
 
 #include "engine.cuh"
+#include "host_numa.h"
 #include "generic_smem.cuh"
 #include "fast_tiers.cuh"
 #include "mixed_kernels.cuh"
@@ -18,12 +19,13 @@
 #include "../../include/invgpu.h"
 #include "../../include/inverse_gpu.h"
 #include "../../include/gauss_gpu.h"
+#include "../../include/helper_gpu.h"
 
 namespace invgpu {
 
 std::atomic<long long> g_launches{0};
 
-std::mutex &engine_mutex() {
+std::mutex &init_mutex() {
     static std::mutex m;
     return m;
 }
@@ -35,15 +37,17 @@ DeviceState *device_state(int *err) {
     if (e != cudaSuccess) { *err = (int)e; return nullptr; }
     if (dev < 0 || dev >= 64) { *err = INVGPU_EARG; return nullptr; }
     DeviceState *ds = &states[dev];
-    if (ds->dev != dev) {
-        std::lock_guard<std::mutex> lk(engine_mutex());
-        if (ds->dev != dev) {
-            cudaDeviceProp p;
-            e = cudaGetDeviceProperties(&p, dev);
+    if (ds->dev.load(std::memory_order_acquire) != dev) {
+        std::lock_guard<std::mutex> lk(init_mutex());
+        if (ds->dev.load(std::memory_order_relaxed) != dev) {
+            int sms = 0, optin = 0;
+            e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            if (e == cudaSuccess) e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
             if (e != cudaSuccess) { *err = (int)e; return nullptr; }
-            ds->sms = p.multiProcessorCount;
-            ds->smem_optin = p.sharedMemPerBlockOptin;
-            ds->dev = dev;
+            ds->sms = sms;
+            ds->smem_optin = (size_t)optin;
+            ds->numa_node = numa_node_of_device(dev);
+            ds->dev.store(dev, std::memory_order_release);
         }
     }
     return ds;
@@ -52,16 +56,30 @@ DeviceState *device_state(int *err) {
 // ------------------------------------------------------------------------------------------
 // kernel dispatch
 // ------------------------------------------------------------------------------------------
-#define INVGPU_LAUNCH(kern, block, smem, blocks_needed, ...)                                  \
-    do {                                                                                       \
-        int grid__ = 0;                                                                        \
-        int rc__ = persistent_grid(kern, block, smem, blocks_needed, ds, &grid__);             \
-        if (rc__ == -2) return INVGPU_EUNSUPPORTED;                                            \
-        if (rc__) return rc__;                                                                 \
-        kern<<<grid__, block, smem, st>>>(__VA_ARGS__);                                        \
-        g_launches.fetch_add(1, std::memory_order_relaxed);                                    \
-        return (int)cudaGetLastError();                                                        \
-    } while (0)
+// Launch one of the any-n kernels of generic_smem.cuh.  `slab` = bytes of one matrix' working copy, `fixed` = bytes
+// of shared memory needed besides it (pivot log), `per_cta` = matrices per CTA.  When the slabs fit the opt-in
+// shared memory they live there; otherwise (fp64 / large n) in a per-stream global scratch, one slab per resident
+// CTA, and the kernel gets its base as `gws`.
+template <typename T, typename Kern, typename... Args>
+static int launch_generic(Kern kern, int block, size_t slab, size_t fixed, int per_cta, i64 batch, DeviceState *ds,
+                          cudaStream_t st, Args... args) {
+    const i64 blocks_needed = (batch + per_cta - 1) / per_cta;
+    size_t smem = per_cta * slab + fixed;
+    const bool global_ws = smem > ds->smem_optin;
+    if (global_ws) smem = fixed;
+    int grid = 0;
+    int rc = persistent_grid(kern, block, smem, blocks_needed, ds, &grid);
+    if (rc == -2) return INVGPU_EUNSUPPORTED;
+    if (rc) return rc;
+    void *gws = nullptr;
+    if (global_ws) {
+        rc = ensure_gp_scratch(ds, (size_t)grid * per_cta * slab, st, &gws);
+        if (rc) return rc;
+    }
+    kern<<<grid, block, smem, st>>>(args..., (T *)gws);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return (int)cudaGetLastError();
+}
 
 template <typename T, typename IO, int STAGES>
 static int run_spd(IO io, int n, i64 batch, int *dInfo, cudaStream_t st) {
@@ -72,16 +90,10 @@ static int run_spd(IO io, int n, i64 batch, int *dInfo, cudaStream_t st) {
     if (!ds) return err;
     int rc = fast_spd<T, IO, STAGES>(io, n, batch, dInfo, st, ds);
     if (rc != INVGPU_NO_FAST_PATH) return rc;
-    if (n <= 32) {
-        INVGPU_LAUNCH((spd_generic_kernel<T, 32, IO, STAGES>), 128, 4 * (size_t)packed_row(n) * sizeof(T),
-                      (batch + 3) / 4, io, n, batch, dInfo);
-    } else if (n <= 128) {
-        INVGPU_LAUNCH((spd_generic_kernel<T, 128, IO, STAGES>), 128, (size_t)packed_row(n) * sizeof(T), batch,
-                      io, n, batch, dInfo);
-    } else if (n <= 256) {
-        INVGPU_LAUNCH((spd_generic_kernel<T, 256, IO, STAGES>), 256, (size_t)packed_row(n) * sizeof(T), batch,
-                      io, n, batch, dInfo);
-    }
+    const size_t slab = (size_t)packed_row(n) * sizeof(T);
+    if (n <= 32) return launch_generic<T>(spd_generic_kernel<T, 32, IO, STAGES>, 128, slab, 0, 4, batch, ds, st, io, n, batch, dInfo);
+    if (n <= 128) return launch_generic<T>(spd_generic_kernel<T, 128, IO, STAGES>, 128, slab, 0, 1, batch, ds, st, io, n, batch, dInfo);
+    if (n <= 256) return launch_generic<T>(spd_generic_kernel<T, 256, IO, STAGES>, 256, slab, 0, 1, batch, ds, st, io, n, batch, dInfo);
     return INVGPU_EUNSUPPORTED;
 }
 
@@ -94,14 +106,10 @@ static int run_general(IO io, int n, i64 batch, int *dInfo, cudaStream_t st) {
     if (!ds) return err;
     int rc = fast_general<T, IO>(io, n, batch, dInfo, st, ds);
     if (rc != INVGPU_NO_FAST_PATH) return rc;
-    const size_t slab = (size_t)n * (n | 1) * sizeof(T) + (size_t)n * sizeof(int);
-    if (n <= 32) {
-        INVGPU_LAUNCH((gj_generic_kernel<T, 32, IO>), 128, 4 * slab, (batch + 3) / 4, io, n, batch, dInfo);
-    } else if (n <= 128) {
-        INVGPU_LAUNCH((gj_generic_kernel<T, 128, IO>), 128, slab, batch, io, n, batch, dInfo);
-    } else if (n <= 256) {
-        INVGPU_LAUNCH((gj_generic_kernel<T, 256, IO>), 256, slab, batch, io, n, batch, dInfo);
-    }
+    const size_t slab = (size_t)n * (n | 1) * sizeof(T), piv = (size_t)n * sizeof(int);
+    if (n <= 32) return launch_generic<T>(gj_generic_kernel<T, 32, IO>, 128, slab, 4 * piv, 4, batch, ds, st, io, n, batch, dInfo);
+    if (n <= 128) return launch_generic<T>(gj_generic_kernel<T, 128, IO>, 128, slab, piv, 1, batch, ds, st, io, n, batch, dInfo);
+    if (n <= 256) return launch_generic<T>(gj_generic_kernel<T, 256, IO>, 256, slab, piv, 1, batch, ds, st, io, n, batch, dInfo);
     return INVGPU_EUNSUPPORTED;
 }
 
@@ -118,13 +126,9 @@ static int run_gp(GpIO<T> io, int n, i64 batch, int *dInfo, cudaStream_t st) {
     int rc = fast_gp<T>(io, n, batch, dInfo, st, ds);
     if (rc != INVGPU_NO_FAST_PATH) return rc;
     const size_t slab = ((size_t)packed_row(n) + 2 * (size_t)n) * sizeof(T);
-    if (n <= 32) {
-        INVGPU_LAUNCH((gp_generic_kernel<T, 32>), 128, 4 * slab, (batch + 3) / 4, io, n, batch, dInfo);
-    } else if (n <= 128) {
-        INVGPU_LAUNCH((gp_generic_kernel<T, 128>), 128, slab, batch, io, n, batch, dInfo);
-    } else if (n <= 256) {
-        INVGPU_LAUNCH((gp_generic_kernel<T, 256>), 256, slab, batch, io, n, batch, dInfo);
-    }
+    if (n <= 32) return launch_generic<T>(gp_generic_kernel<T, 32>, 128, slab, 0, 4, batch, ds, st, io, n, batch, dInfo);
+    if (n <= 128) return launch_generic<T>(gp_generic_kernel<T, 128>, 128, slab, 0, 1, batch, ds, st, io, n, batch, dInfo);
+    if (n <= 256) return launch_generic<T>(gp_generic_kernel<T, 256>, 256, slab, 0, 1, batch, ds, st, io, n, batch, dInfo);
     return INVGPU_EUNSUPPORTED;
 }
 
@@ -154,36 +158,85 @@ static bool is_pinned(const void *p) {
     return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
 }
 
-static int ensure_pipeline(DeviceState *ds, size_t slot_bytes) {
-    if (!ds->streams_ready) {
-        INVGPU_TRY(cudaStreamCreateWithFlags(&ds->s_in, cudaStreamNonBlocking));
-        INVGPU_TRY(cudaStreamCreateWithFlags(&ds->s_comp, cudaStreamNonBlocking));
-        INVGPU_TRY(cudaStreamCreateWithFlags(&ds->s_out, cudaStreamNonBlocking));
-        for (int i = 0; i < DeviceState::kSlots; ++i) {
-            INVGPU_TRY(cudaEventCreateWithFlags(&ds->ev_in[i], cudaEventDisableTiming));
-            INVGPU_TRY(cudaEventCreateWithFlags(&ds->ev_comp[i], cudaEventDisableTiming));
-            INVGPU_TRY(cudaEventCreateWithFlags(&ds->ev_out[i], cudaEventDisableTiming));
-        }
-        for (int i = 0; i < DeviceState::kMixedTiers; ++i) INVGPU_TRY(cudaEventCreateWithFlags(&ds->ev_mixed[i], cudaEventDisableTiming));
-        ds->streams_ready = true;
+static int ensure_streams(DeviceState *ds) {
+    if (ds->streams_ready) return 0;
+    INVGPU_TRY(cudaStreamCreateWithFlags(&ds->s_in, cudaStreamNonBlocking));
+    INVGPU_TRY(cudaStreamCreateWithFlags(&ds->s_comp, cudaStreamNonBlocking));
+    INVGPU_TRY(cudaStreamCreateWithFlags(&ds->s_out, cudaStreamNonBlocking));
+    for (int i = 0; i < DeviceState::kSlots; ++i) {
+        INVGPU_TRY(cudaEventCreateWithFlags(&ds->ev_in[i], cudaEventDisableTiming));
+        INVGPU_TRY(cudaEventCreateWithFlags(&ds->ev_comp[i], cudaEventDisableTiming));
+        INVGPU_TRY(cudaEventCreateWithFlags(&ds->ev_out[i], cudaEventDisableTiming));
     }
+    for (int i = 0; i < DeviceState::kMixedTiers; ++i) INVGPU_TRY(cudaEventCreateWithFlags(&ds->ev_mixed[i], cudaEventDisableTiming));
+    for (int i = 0; i < DeviceState::kMixedRing; ++i) {
+        INVGPU_TRY(cudaEventCreateWithFlags(&ds->mixed[i].done, cudaEventDisableTiming));
+        INVGPU_TRY(cudaEventCreateWithFlags(&ds->mixed[i].uploaded, cudaEventDisableTiming));
+    }
+    ds->streams_ready = true;
+    return 0;
+}
+
+// The calling host thread feeds this device: keep it (once) on the CPUs of the device's NUMA node, so that the
+// staging memcpys of pageable buffers and the first touch of the pinned ring stay local (host_numa.h).
+static void bind_feeder_thread(DeviceState *ds) {
+    static thread_local int bound_dev = -1;
+    const int dev = ds->dev.load(std::memory_order_relaxed);
+    if (bound_dev == dev) return;
+    bound_dev = dev;
+    numa_bind_thread_to_device(dev);
+}
+
+static int ensure_pipeline(DeviceState *ds, size_t slot_bytes, size_t ring_bytes) {
+    int rc = ensure_streams(ds);
+    if (rc) return rc;
+    const int dev = ds->dev.load(std::memory_order_relaxed);
     if (ds->d_ws_bytes < slot_bytes) {
         for (int i = 0; i < DeviceState::kSlots; ++i) {
             if (ds->d_ws[i]) cudaFree(ds->d_ws[i]);
-            if (ds->h_ring[i]) cudaFreeHost(ds->h_ring[i]);
-            ds->d_ws[i] = nullptr; ds->h_ring[i] = nullptr;
+            ds->d_ws[i] = nullptr;
         }
-        ds->d_ws_bytes = 0; ds->h_ring_bytes = 0;
+        ds->d_ws_bytes = 0;
+        for (int i = 0; i < DeviceState::kSlots; ++i) INVGPU_TRY(cudaMalloc(&ds->d_ws[i], slot_bytes));
+        ds->d_ws_bytes = slot_bytes;
+    }
+    // the pinned ring stages pageable user buffers and the info words; pinned user buffers are DMA'd directly, so
+    // a caller that only passes pinned memory never pays for (or page-locks) a full-size ring
+    if (ds->h_ring_bytes < ring_bytes) {
         for (int i = 0; i < DeviceState::kSlots; ++i) {
-            INVGPU_TRY(cudaMalloc(&ds->d_ws[i], slot_bytes));
-            INVGPU_TRY(cudaHostAlloc(&ds->h_ring[i], slot_bytes, cudaHostAllocDefault));
+            if (ds->h_ring[i]) cudaFreeHost(ds->h_ring[i]);
+            ds->h_ring[i] = nullptr;
         }
-        ds->d_ws_bytes = slot_bytes; ds->h_ring_bytes = slot_bytes;
+        ds->h_ring_bytes = 0;
+        for (int i = 0; i < DeviceState::kSlots; ++i) INVGPU_TRY(numa_host_alloc(&ds->h_ring[i], ring_bytes, dev, cudaHostAllocDefault));
+        ds->h_ring_bytes = ring_bytes;
     }
     return 0;
 }
 
 static size_t g_chunk_bytes = 0;   // 0 = default; settable through INVGPU_CHUNK_MB
+
+// Phase timers of the reference's `make log=1` build (-DDETAILED_LOGGING; include/timer.h:8-9 and e.g.
+// src/gauss/batched_invert.cu:114-171): every *_gpu wrapper prints "<name>_mem_htod / _ker / _mem_dtoh,batch,n,ms,ns".
+// Here the three phases overlap chunk by chunk, so what is reported per phase is the BUSY time of its stream
+// (sum over chunks, CUDA events).  On when built with -DDETAILED_LOGGING (make log=1) or INVGPU_DETAILED_LOGGING=1.
+struct PhaseTimes { double htod_ms = 0, ker_ms = 0, dtoh_ms = 0; };
+static thread_local PhaseTimes g_phases;
+static bool detailed_logging() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("INVGPU_DETAILED_LOGGING");
+#ifdef DETAILED_LOGGING
+        v = (e && !strcmp(e, "0")) ? 0 : 1;
+#else
+        v = (e && atoi(e) > 0) ? 1 : 0;
+#endif
+    }
+    return v == 1;
+}
+static void phase_log(const char *name, const char *phase, int batch, int n, double ms) {
+    printf("%s%s,%d,%d,%.4f,%lu\r\n", name, phase, batch, n, ms, (unsigned long)(ms * 1e6));
+}
 
 // launch(dptrs, count, stream): dptrs[i] is the device address of array i for this chunk.
 template <typename LaunchFn>
@@ -194,14 +247,19 @@ static int host_pipeline(std::vector<HostArr> &arrs, i64 batch, int *info, int *
     int err = 0;
     DeviceState *ds = device_state(&err);
     if (!ds) return err;
-    std::lock_guard<std::mutex> lk(engine_mutex());
+    std::lock_guard<std::mutex> lk(ds->mu);          // per device: other devices' pipelines run concurrently
+    bind_feeder_thread(ds);
 
-    // info rides along as one more output array (4 bytes per unit)
-    HostArr ia; ia.in = nullptr; ia.out = (char *)info; ia.unit = sizeof(int); ia.pinned = info && is_pinned(info); ia.off = 0;
+    // info rides along as one more output array (4 bytes per unit); it has its own small ring region
+    HostArr ia; ia.in = nullptr; ia.out = (char *)info; ia.unit = sizeof(int); ia.pinned = false; ia.off = 0;
     arrs.push_back(ia);
     size_t unit_total = 0;
+    bool any_pageable = false;
     for (auto &a : arrs) {
-        if (&a != &arrs.back()) a.pinned = is_pinned(a.in ? (const void *)a.in : (const void *)a.out);
+        if (&a != &arrs.back()) {
+            a.pinned = is_pinned(a.in ? (const void *)a.in : (const void *)a.out);
+            if (!a.pinned) any_pageable = true;
+        }
         unit_total += a.unit;
     }
     size_t target = g_chunk_bytes;
@@ -212,13 +270,18 @@ static int host_pipeline(std::vector<HostArr> &arrs, i64 batch, int *info, int *
     i64 cu = (i64)(target / unit_total);
     if (cu < 1) cu = 1;
     if (cu > batch) cu = batch;
+    // slot layout: the info words first (so that a ring that only stages info stays small), then the arrays
     size_t slot_bytes = 0;
-    for (auto &a : arrs) { a.off = slot_bytes; slot_bytes += (a.unit * (size_t)cu + 255) & ~(size_t)255; }
-    int rc = ensure_pipeline(ds, slot_bytes);
+    arrs.back().off = 0; slot_bytes = ((size_t)cu * sizeof(int) + 255) & ~(size_t)255;
+    for (auto &a : arrs) { if (&a == &arrs.back()) continue; a.off = slot_bytes; slot_bytes += (a.unit * (size_t)cu + 255) & ~(size_t)255; }
+    int rc = ensure_pipeline(ds, slot_bytes, any_pageable ? slot_bytes : (((size_t)cu * sizeof(int) + 255) & ~(size_t)255));
     if (rc) return rc;
 
     const i64 nchunks = (batch + cu - 1) / cu;
     const int S = DeviceState::kSlots;
+    const bool logging = detailed_logging();
+    std::vector<cudaEvent_t> tev;                    // six timing events per chunk when logging
+    auto stamp = [&](cudaStream_t st) { if (logging) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); tev.push_back(e); } };
     auto drain = [&](i64 c) -> int {
         const int slot = (int)(c % S);
         INVGPU_TRY(cudaEventSynchronize(ds->ev_out[slot]));
@@ -240,38 +303,62 @@ static int host_pipeline(std::vector<HostArr> &arrs, i64 batch, int *info, int *
         }
         return 0;
     };
+    // an error in the middle of the stream of chunks: nothing may still be reading the caller's buffers or the
+    // ring when we return, so wait for everything that has been queued
+    auto fail = [&](int code) -> int {
+        cudaStreamSynchronize(ds->s_in); cudaStreamSynchronize(ds->s_comp); cudaStreamSynchronize(ds->s_out);
+        cudaGetLastError();
+        return code;
+    };
+#define INVGPU_PIPE_TRY(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) return fail((int)e__); } while (0)
 
     for (i64 c = 0; c < nchunks; ++c) {
         const int slot = (int)(c % S);
-        if (c >= S) { rc = drain(c - S); if (rc) return rc; }
+        if (c >= S) { rc = drain(c - S); if (rc) return fail(rc); }
         const i64 first = c * cu;
         const i64 cnt = (first + cu <= batch) ? cu : batch - first;
         char *dbase = (char *)ds->d_ws[slot];
         char *hbase = (char *)ds->h_ring[slot];
         void *dptrs[16];
         int na = 0;
-        for (auto &a : arrs) dptrs[na++] = dbase + a.off;
+        for (auto &a : arrs) { dptrs[na] = dbase + a.off; ++na; }
+        stamp(ds->s_in);
         for (auto &a : arrs) {
             if (!a.in) continue;
             const char *src = a.in + (size_t)first * a.unit;
             if (!a.pinned) { memcpy(hbase + a.off, src, (size_t)cnt * a.unit); src = hbase + a.off; }
-            INVGPU_TRY(cudaMemcpyAsync(dbase + a.off, src, (size_t)cnt * a.unit, cudaMemcpyHostToDevice, ds->s_in));
+            INVGPU_PIPE_TRY(cudaMemcpyAsync(dbase + a.off, src, (size_t)cnt * a.unit, cudaMemcpyHostToDevice, ds->s_in));
         }
-        INVGPU_TRY(cudaEventRecord(ds->ev_in[slot], ds->s_in));
-        INVGPU_TRY(cudaStreamWaitEvent(ds->s_comp, ds->ev_in[slot], 0));
+        stamp(ds->s_in);
+        INVGPU_PIPE_TRY(cudaEventRecord(ds->ev_in[slot], ds->s_in));
+        INVGPU_PIPE_TRY(cudaStreamWaitEvent(ds->s_comp, ds->ev_in[slot], 0));
+        stamp(ds->s_comp);
         rc = launch(dptrs, cnt, ds->s_comp);
-        if (rc) return rc;
-        INVGPU_TRY(cudaEventRecord(ds->ev_comp[slot], ds->s_comp));
-        INVGPU_TRY(cudaStreamWaitEvent(ds->s_out, ds->ev_comp[slot], 0));
+        if (rc) return fail(rc);
+        stamp(ds->s_comp);
+        INVGPU_PIPE_TRY(cudaEventRecord(ds->ev_comp[slot], ds->s_comp));
+        INVGPU_PIPE_TRY(cudaStreamWaitEvent(ds->s_out, ds->ev_comp[slot], 0));
+        stamp(ds->s_out);
         for (auto &a : arrs) {
             if (a.in || (!a.out && &a != &arrs.back())) continue;
             const bool is_info = (&a == &arrs.back());
             char *dst = (a.pinned && !is_info) ? a.out + (size_t)first * a.unit : hbase + a.off;
-            INVGPU_TRY(cudaMemcpyAsync(dst, dbase + a.off, (size_t)cnt * a.unit, cudaMemcpyDeviceToHost, ds->s_out));
+            INVGPU_PIPE_TRY(cudaMemcpyAsync(dst, dbase + a.off, (size_t)cnt * a.unit, cudaMemcpyDeviceToHost, ds->s_out));
         }
-        INVGPU_TRY(cudaEventRecord(ds->ev_out[slot], ds->s_out));
+        stamp(ds->s_out);
+        INVGPU_PIPE_TRY(cudaEventRecord(ds->ev_out[slot], ds->s_out));
     }
-    for (i64 c = (nchunks > S ? nchunks - S : 0); c < nchunks; ++c) { rc = drain(c); if (rc) return rc; }
+    for (i64 c = (nchunks > S ? nchunks - S : 0); c < nchunks; ++c) { rc = drain(c); if (rc) return fail(rc); }
+#undef INVGPU_PIPE_TRY
+    if (logging) {
+        g_phases = PhaseTimes();
+        for (size_t i = 0; i + 5 < tev.size(); i += 6) {
+            float h = 0, k = 0, d = 0;
+            cudaEventElapsedTime(&h, tev[i], tev[i + 1]); cudaEventElapsedTime(&k, tev[i + 2], tev[i + 3]); cudaEventElapsedTime(&d, tev[i + 4], tev[i + 5]);
+            g_phases.htod_ms += h; g_phases.ker_ms += k; g_phases.dtoh_ms += d;
+        }
+        for (cudaEvent_t e : tev) cudaEventDestroy(e);
+    }
     return 0;
 }
 
@@ -326,14 +413,8 @@ static int launch_mixed_bucket(const MixedItem *dItems, i64 count, int nmax, int
     auto kern = mixed_spd_kernel<T, G>;
     const int block = G <= 32 ? 256 : G;
     const int per_unit = G <= 32 ? 8 : 1;
-    const size_t smem = (size_t)per_unit * packed_row(nmax) * sizeof(T);
-    int grid = 0;
-    int rc = persistent_grid(kern, block, smem, (count + per_unit - 1) / per_unit, ds, &grid);
-    if (rc == -2) return INVGPU_EUNSUPPORTED;
-    if (rc) return rc;
-    kern<<<grid, block, smem, st>>>(dItems, count, nmax, dInfo, dTicket);
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-    return (int)cudaGetLastError();
+    return launch_generic<T>(kern, block, (size_t)packed_row(nmax) * sizeof(T), 0, per_unit, count, ds, st,
+                             dItems, count, nmax, dInfo, dTicket);
 }
 
 template <typename T>
@@ -388,22 +469,25 @@ static int run_mixed_spd(T *const *hIn, T *const *hOut, const int *hN, i64 count
                 if (hist[n] && n > nmax[b]) nmax[b] = n;
             }
     }
-    std::lock_guard<std::mutex> lk(engine_mutex());
-    int rc = ensure_pipeline(ds, 0);                          // streams + events
+    std::lock_guard<std::mutex> lk(ds->mu);
+    int rc = ensure_streams(ds);
     if (rc) return rc;
     constexpr size_t HDR = 256;                               // tickets of the generic kernels
     const size_t need = (size_t)count * sizeof(MixedItem) + HDR;
-    if (ds->mixed_bytes < need) {
-        if (ds->d_mixed) cudaFree(ds->d_mixed);
-        if (ds->h_mixed) cudaFreeHost(ds->h_mixed);
-        ds->d_mixed = nullptr; ds->h_mixed = nullptr; ds->mixed_bytes = 0;
-        INVGPU_TRY(cudaMalloc(&ds->d_mixed, need));
-        INVGPU_TRY(cudaHostAlloc(&ds->h_mixed, need, cudaHostAllocDefault));
-        ds->mixed_bytes = need;
+    // work list + tickets of THIS call: the next buffer of a small ring; it is free again when the event recorded
+    // behind the last tier kernel of the call that used it before has completed (calls on other streams or from
+    // other host threads therefore never overwrite a list that kernels still read)
+    DeviceState::MixedBuf &mb = ds->mixed[ds->mixed_next++ % DeviceState::kMixedRing];
+    INVGPU_TRY(cudaEventSynchronize(mb.done));
+    if (mb.bytes < need) {
+        if (mb.d) cudaFree(mb.d);
+        if (mb.h) cudaFreeHost(mb.h);
+        mb.d = nullptr; mb.h = nullptr; mb.bytes = 0;
+        INVGPU_TRY(cudaMalloc(&mb.d, need));
+        INVGPU_TRY(numa_host_alloc(&mb.h, need, ds->dev.load(std::memory_order_relaxed), cudaHostAllocDefault));
+        mb.bytes = need;
     }
-    // the staging buffer is reused: wait for the previous call's upload
-    INVGPU_TRY(cudaEventSynchronize(ds->ev_in[0]));
-    char *h = (char *)ds->h_mixed;
+    char *h = (char *)mb.h;
     memset(h, 0, HDR);
     MixedItem *items = (MixedItem *)(h + HDR);
     // thread t writes the items of order n at first[n] + (items of order n owned by threads < t)
@@ -420,8 +504,8 @@ static int run_mixed_spd(T *const *hIn, T *const *hOut, const int *hN, i64 count
     size_t off = HDR;
     for (int b = 0; b < NT; ++b) { start[b] = off; off += (size_t)bcount[b] * sizeof(MixedItem); }
     const auto t_plan1 = std::chrono::steady_clock::now();
-    INVGPU_TRY(cudaMemcpyAsync(ds->d_mixed, h, off, cudaMemcpyHostToDevice, st));
-    INVGPU_TRY(cudaEventRecord(ds->ev_in[0], st));
+    INVGPU_TRY(cudaMemcpyAsync(mb.d, h, off, cudaMemcpyHostToDevice, st));
+    INVGPU_TRY(cudaEventRecord(mb.uploaded, st));
     // Tiers run concurrently on the engine's three streams (big matrices first).  Each tier is one persistent
     // grid: the padded sweep kernel (every item of a tier costs the same, so its grid-stride work split is
     // balanced by construction) or, where no padded tier exists (fp64 above 128), the any-n shared-memory
@@ -429,11 +513,12 @@ static int run_mixed_spd(T *const *hIn, T *const *hOut, const int *hN, i64 count
     static int generic_only = -1;
     if (generic_only < 0) { const char *e = getenv("INVGPU_MIXED_KERNEL"); generic_only = (e && !strcmp(e, "generic")) ? 1 : 0; }
     cudaStream_t lanes[3] = {ds->s_in, ds->s_comp, ds->s_out};
-    char *d = (char *)ds->d_mixed;
-    for (int b = NT - 1; b >= 0; --b) {
+    char *d = (char *)mb.d;
+    int result = 0;
+    for (int b = NT - 1; b >= 0 && !result; --b) {
         if (bcount[b] == 0) continue;
         cudaStream_t lane = lanes[b % 3];
-        INVGPU_TRY(cudaStreamWaitEvent(lane, ds->ev_in[0], 0));
+        if ((rc = (int)cudaStreamWaitEvent(lane, mb.uploaded, 0))) { result = rc; break; }
         const MixedItem *di = (const MixedItem *)(d + start[b]);
         unsigned long long *tk = (unsigned long long *)(d + 16 * b);
         cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -445,16 +530,19 @@ static int run_mixed_spd(T *const *hIn, T *const *hOut, const int *hN, i64 count
             else if (hi[b] <= 128) rc = launch_mixed_bucket<T, 128>(di, bcount[b], nmax[b], dInfo, tk, lane, ds);
             else rc = launch_mixed_bucket<T, 256>(di, bcount[b], nmax[b], dInfo, tk, lane, ds);
         }
-        if (rc) return rc;
         if (timing) {                                          // serialises the tiers: diagnostics only
             cudaEventRecord(e1, lane); cudaEventSynchronize(e1);
             float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
             fprintf(stderr, "[invgpu mixed] tier <=%d: %lld matrices, nmax %d, %.3f ms\n", hi[b], (long long)bcount[b], nmax[b], ms);
             cudaEventDestroy(e0); cudaEventDestroy(e1);
         }
-        INVGPU_TRY(cudaEventRecord(ds->ev_mixed[b], lane));
-        INVGPU_TRY(cudaStreamWaitEvent(st, ds->ev_mixed[b], 0));
+        // join the lane into the caller's stream even when this tier failed to launch: earlier tiers are running
+        cudaEventRecord(ds->ev_mixed[b], lane);
+        cudaStreamWaitEvent(st, ds->ev_mixed[b], 0);
+        if (rc) result = rc;
     }
+    cudaEventRecord(mb.done, st);                              // behind every tier kernel of this call
+    if (result) return result;
     if (timing)
         fprintf(stderr, "[invgpu mixed] host planning %.3f ms for %lld matrices\n",
                 std::chrono::duration<double, std::milli>(t_plan1 - t_plan0).count(), (long long)count);
@@ -594,9 +682,26 @@ int invgpu_gp_host_f64(int n, const double *As, const double *Bs, const double *
     int bad[2]; return finish_host(host_gp<double>(n, As, Bs, Cs, Ds, Es, Means, Variances, batch, info, bad), info, bad);
 }
 
+int invgpu_xfer_roundtrip_host(const void *in, void *out, unsigned long long unit_bytes, invgpu_i64 batch) {
+    if (!in || !out || unit_bytes == 0) return INVGPU_EARG;
+    std::vector<HostArr> arrs(2);
+    arrs[0] = HostArr{(const char *)in, nullptr, (size_t)unit_bytes, false, 0};
+    arrs[1] = HostArr{nullptr, (char *)out, (size_t)unit_bytes, false, 0};
+    return host_pipeline(arrs, batch, nullptr, nullptr, [&](void **d, i64 cnt, cudaStream_t st) -> int {
+        cudaError_t e = cudaMemcpyAsync(d[1], d[0], (size_t)cnt * unit_bytes, cudaMemcpyDeviceToDevice, st);
+        if (e == cudaSuccess) e = cudaMemsetAsync(d[2], 0, (size_t)cnt * sizeof(int), st);
+        return (int)e;
+    });
+}
+
+int invgpu_device_numa_node(int device) { return numa_node_of_device(device); }
+
 void *invgpu_host_alloc(unsigned long long bytes) {
     void *p = nullptr;
-    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    // pages are first-touched on the NUMA node of the calling thread's current device (host_numa.h)
+    if (numa_host_alloc(&p, bytes, dev, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
     return p;
 }
 void invgpu_host_free(void *p) { if (p) cudaFreeHost(p); }
@@ -605,7 +710,7 @@ void invgpu_release_workspace(void) {
     int err = 0;
     DeviceState *ds = device_state(&err);
     if (!ds) return;
-    std::lock_guard<std::mutex> lk(engine_mutex());
+    std::lock_guard<std::mutex> lk(ds->mu);
     cudaDeviceSynchronize();
     for (int i = 0; i < DeviceState::kSlots; ++i) {
         if (ds->d_ws[i]) cudaFree(ds->d_ws[i]);
@@ -613,6 +718,15 @@ void invgpu_release_workspace(void) {
         ds->d_ws[i] = nullptr; ds->h_ring[i] = nullptr;
     }
     ds->d_ws_bytes = 0; ds->h_ring_bytes = 0;
+    for (auto &mb : ds->mixed) {
+        if (mb.d) cudaFree(mb.d);
+        if (mb.h) cudaFreeHost(mb.h);
+        mb.d = nullptr; mb.h = nullptr; mb.bytes = 0;
+    }
+    std::lock_guard<std::mutex> lk2(ds->scratch_mu);
+    for (auto &e : ds->gp_scratch) if (e.p) cudaFree(e.p);
+    for (void *p : ds->retired) cudaFree(p);
+    ds->gp_scratch.clear(); ds->retired.clear();
 }
 
 // ==========================================================================================
@@ -641,22 +755,32 @@ static void legacy_check(int rc, const char *what, const int *bad, const char *s
 static const char *kCholMsg = "Error code %d in cholesky factorization";   // reference src/inverse.c:94
 static const char *kLuMsg = "Error code %d in LU-decomposition";           // reference src/inverse.c:64
 
-#define LEGACY_HOST_SPD(name)                                                                   \
+// `timer` = the reference's TIMER_LOG prefix of that wrapper (e.g. src/inverse_cholesky_gpu.cu:450-452)
+static void legacy_phase_lines(const char *timer, int batch, int n) {
+    if (!detailed_logging()) return;
+    phase_log(timer, "_mem_htod", batch, n, g_phases.htod_ms);
+    phase_log(timer, "_ker", batch, n, g_phases.ker_ms);
+    phase_log(timer, "_mem_dtoh", batch, n, g_phases.dtoh_ms);
+}
+
+#define LEGACY_HOST_SPD(name, timer)                                                            \
     void name(cublasHandle_t, int n, Array As, Array aInvs, int batchSize) {                    \
         int bad[2];                                                                             \
         int rc = host_inverse<float, true>(As, aInvs, n, batchSize, nullptr, bad);              \
         legacy_check(rc, #name, bad, kCholMsg);                                                 \
+        legacy_phase_lines(timer, batchSize, n);                                                \
     }
-LEGACY_HOST_SPD(inverse_cholesky_batched_gpu)
-LEGACY_HOST_SPD(inverse_cholesky_mm_batched_gpu)
-LEGACY_HOST_SPD(inverse_cholesky_mm2_batched_gpu)
-LEGACY_HOST_SPD(inverse_cholesky_stride_batched_gpu)
+LEGACY_HOST_SPD(inverse_cholesky_batched_gpu, "decompose_cholesky_batched_gpu")
+LEGACY_HOST_SPD(inverse_cholesky_mm_batched_gpu, "decompose_cholesky_mm_batched_gpu")
+LEGACY_HOST_SPD(inverse_cholesky_mm2_batched_gpu, "cholesky_mm2_batched_gpu")
+LEGACY_HOST_SPD(inverse_cholesky_stride_batched_gpu, "inverse_cholesky_stride_batched_gpu")
 
 #define LEGACY_HOST_GENERAL(name)                                                               \
     void name(cublasHandle_t, int n, Array As, Array aInvs, int batchSize) {                    \
         int bad[2];                                                                             \
         int rc = host_inverse<float, false>(As, aInvs, n, batchSize, nullptr, bad);             \
         legacy_check(rc, #name, bad, kLuMsg);                                                   \
+        legacy_phase_lines(#name, batchSize, n);                                                \
     }
 LEGACY_HOST_GENERAL(inverse_gauss_batched_gpu)
 LEGACY_HOST_GENERAL(inverse_lu_cuda_batched_gpu)
@@ -688,15 +812,41 @@ void inverse_lu_cuda_batched_device(cublasHandle_t, int N, Array *devAs, Array *
     legacy_check(rc, "inverse_lu_cuda_batched_device", nullptr, kLuMsg);
 }
 
+// reference src/helper.cu:103-118: ONE pitched allocation for the batch, per-matrix pointers into a host array
+cudaError_t batchedCudaMalloc(Array *devArrayPtr, size_t *pitch, size_t arraySize, int batchSize) {
+    if (!devArrayPtr || !pitch || batchSize < 0) return cudaErrorInvalidValue;
+    void *base = nullptr;
+    const cudaError_t e = cudaMallocPitch(&base, pitch, arraySize, (size_t)batchSize);
+    if (e != cudaSuccess) return e;
+    for (int i = 0; i < batchSize; ++i) devArrayPtr[i] = (Array)((char *)base + (size_t)i * *pitch);
+    return cudaSuccess;
+}
+
 void calcluateMeanGPU(int n, Array As, Array Bs, Array Cs, Array Ds, Array Means, int batchSize) {
     int bad[2];
     int rc = host_gp<float>(n, As, Bs, Cs, Ds, nullptr, Means, nullptr, batchSize, nullptr, bad);
     legacy_check(rc, "calcluateMeanGPU", bad, kCholMsg);
+    if (detailed_logging()) {       // src/gauss_bench.cu:251-256: six phases; add / mul / dot are fused into `inv` here
+        phase_log("calculate_mean_gpu", "_mem_htod", batchSize, n, g_phases.htod_ms);
+        phase_log("calculate_mean_gpu", "_add", batchSize, n, 0.0);
+        phase_log("calculate_mean_gpu", "_inv", batchSize, n, g_phases.ker_ms);
+        phase_log("calculate_mean_gpu", "_mul", batchSize, n, 0.0);
+        phase_log("calculate_mean_gpu", "_dot", batchSize, n, 0.0);
+        phase_log("calculate_mean_gpu", "_mem_dtoh", batchSize, n, g_phases.dtoh_ms);
+    }
 }
 void calcluateVarianceGPU(int n, Array As, Array Bs, Array Cs, Array Es, Array Variances, int batchSize) {
     int bad[2];
     int rc = host_gp<float>(n, As, Bs, Cs, nullptr, Es, nullptr, Variances, batchSize, nullptr, bad);
     legacy_check(rc, "calcluateVarianceGPU", bad, kCholMsg);
+    if (detailed_logging()) {
+        phase_log("calculate_variance_gpu", "_mem_htod", batchSize, n, g_phases.htod_ms);
+        phase_log("calculate_variance_gpu", "_add", batchSize, n, 0.0);
+        phase_log("calculate_variance_gpu", "_inv", batchSize, n, g_phases.ker_ms);
+        phase_log("calculate_variance_gpu", "_mul", batchSize, n, 0.0);
+        phase_log("calculate_variance_gpu", "_dot", batchSize, n, 0.0);
+        phase_log("calculate_variance_gpu", "_mem_dtoh", batchSize, n, g_phases.dtoh_ms);
+    }
 }
 void calcluateMeanSolveGPU(int n, Array As, Array Bs, Array Cs, Array Ds, Array Means, int batchSize) {
     calcluateMeanGPU(n, As, Bs, Cs, Ds, Means, batchSize);

@@ -25,7 +25,7 @@ extern std::atomic<long long> g_launches;
     } while (0)
 
 struct DeviceState {
-    int dev = -1;
+    std::atomic<int> dev{-1};         // published (release) after sms / smem_optin are written
     int sms = 0;
     size_t smem_optin = 0;
     // host pipeline resources (lazily created, grow-only)
@@ -39,16 +39,43 @@ struct DeviceState {
     static const int kMixedTiers = 9;                         // 16 / 24 / 32 / 48 / 64 / 96 / 128 / 192 / 256
     cudaEvent_t ev_mixed[kMixedTiers];                        // one per tier of the mixed-dimension scheduler
     bool streams_ready = false;
-    // scratch of the fused GP tile kernels (natural-order info recomputation of flagged matrices)
-    void *gp_scratch = nullptr;
-    size_t gp_scratch_bytes = 0;
-    // work lists of the mixed-dimension scheduler (device copy + pinned staging)
-    void *d_mixed = nullptr, *h_mixed = nullptr;
-    size_t mixed_bytes = 0;
+    // scratch of the fused GP tile kernels (natural-order info recomputation of flagged matrices): one buffer per
+    // launch stream, so that GP calls on different streams never share it; a buffer that has to grow is retired
+    // (freed by invgpu_release_workspace), never freed under a launch that may still read it
+    struct Scratch { cudaStream_t st; void *p; size_t bytes; };
+    std::vector<Scratch> gp_scratch;
+    std::vector<void *> retired;
+    std::mutex scratch_mu;
+    // work lists of the mixed-dimension scheduler: a ring of (device copy + pinned staging) pairs, each guarded by
+    // the event recorded after the LAST tier kernel that reads it
+    static const int kMixedRing = 4;
+    struct MixedBuf { void *d = nullptr, *h = nullptr; size_t bytes = 0; cudaEvent_t done = nullptr, uploaded = nullptr; };
+    MixedBuf mixed[kMixedRing];
+    unsigned mixed_next = 0;
+    // one lock per device: the host pipeline and the mixed scheduler of different devices run concurrently
+    std::mutex mu;
+    int numa_node = -1;
 };
 
 DeviceState *device_state(int *err);   // state of the calling thread's current device
-std::mutex &engine_mutex();
+std::mutex &init_mutex();          // first-time initialisation of a DeviceState only
+
+// Per-stream device scratch (natural-order info recomputation of flagged GP matrices; working copies of the any-n
+// kernels when they exceed shared memory).  Launches on one stream are ordered, so they may share a buffer.
+static int ensure_gp_scratch(DeviceState *ds, size_t need, cudaStream_t st, void **out) {
+    std::lock_guard<std::mutex> lk(ds->scratch_mu);
+    DeviceState::Scratch *s = nullptr;
+    for (auto &e : ds->gp_scratch) if (e.st == st) s = &e;
+    if (!s) { ds->gp_scratch.push_back(DeviceState::Scratch{st, nullptr, 0}); s = &ds->gp_scratch.back(); }
+    if (s->bytes < need) {
+        if (s->p) ds->retired.push_back(s->p);        // an earlier launch on this stream may still be running
+        s->p = nullptr; s->bytes = 0;
+        INVGPU_TRY(cudaMalloc(&s->p, need));
+        s->bytes = need;
+    }
+    *out = s->p;
+    return 0;
+}
 
 // Persistent grid: enough CTAs to fill every SM at the kernel's occupancy, never more than the
 // work needs.  148 SMs x resident CTAs per SM on B200.

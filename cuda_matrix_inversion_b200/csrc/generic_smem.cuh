@@ -1,7 +1,9 @@
 // generic_smem.cuh -- any-n kernels: one warp (n <= 32) or one CTA (n <= 256) per matrix,
 // the matrix resident in shared memory.  These are the "every n, both dtypes" tier of the
 // engine: odd sizes, the 256 bucket and anything the register-tiled fast tiers
-// (warp_tier.cuh / cta_tier.cuh) do not instantiate run here.  Same math, same flags.
+// (sweep_kernels.cuh, gj_kernels.cuh, gj_tile_kernels.cuh, tile_kernels.cuh) do not instantiate run here.
+// Same math, same flags.  Where the working copy exceeds one CTA's shared memory (n towards 256) the same
+// kernels run on a per-CTA slab of global memory (`gws`).
 //
 // What is computed (reference file:line each piece replaces):
 //   SPD inverse     A = L L^T, M = L^-1, A^-1 = M^T M      src/inverse_cholesky_gpu.cu:251-354
@@ -150,11 +152,14 @@ enum { SPD_POTRF = 1, SPD_TRTRI = 2, SPD_LAUUM = 4, SPD_INVERSE = 7 };
 
 template <typename T, int G, typename IO, int STAGES>
 __global__ void __launch_bounds__(G <= 32 ? 128 : G)
-spd_generic_kernel(IO io, int n, i64 batch, int *__restrict__ info) {
+spd_generic_kernel(IO io, int n, i64 batch, int *__restrict__ info, T *gws) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int groups = blockDim.x / G;
     const int g = threadIdx.x / G, t = threadIdx.x % G;
-    T *S = reinterpret_cast<T *>(smem_raw) + (size_t)g * packed_row(n);
+    // gws != null: the working copy does not fit shared memory (fp64, n > ~236) and lives in a per-CTA slab of
+    // global memory instead (L2-resident: 148 x 2 slabs of 263 KB); same code, same barriers
+    T *S = gws ? gws + ((size_t)blockIdx.x * groups + g) * packed_row(n)
+               : reinterpret_cast<T *>(smem_raw) + (size_t)g * packed_row(n);
     const int nn = n * n;
 
     for (i64 m0 = (i64)blockIdx.x * groups; m0 < batch; m0 += (i64)gridDim.x * groups) {
@@ -189,15 +194,17 @@ spd_generic_kernel(IO io, int n, i64 batch, int *__restrict__ info) {
 // leading dimension (conflict-free for both "thread per row" and "thread per column").
 template <typename T, int G, typename IO>
 __global__ void __launch_bounds__(G <= 32 ? 128 : G)
-gj_generic_kernel(IO io, int n, i64 batch, int *__restrict__ info) {
+gj_generic_kernel(IO io, int n, i64 batch, int *__restrict__ info, T *gws) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int groups = blockDim.x / G;
     const int g = threadIdx.x / G, t = threadIdx.x % G;
     const int ld = n | 1;
     const size_t slab = (size_t)n * ld;
-    T *S = reinterpret_cast<T *>(smem_raw) + (size_t)g * slab;
+    // gws != null: working copy in a per-CTA slab of global memory (fp32 n > 240, fp64 n > 169), pivot log in smem
+    T *S = gws ? gws + ((size_t)blockIdx.x * groups + g) * slab : reinterpret_cast<T *>(smem_raw) + (size_t)g * slab;
     // after the matrices: per-group pivot log, then reduction scratch (CTA tier only)
-    int *piv = reinterpret_cast<int *>(reinterpret_cast<T *>(smem_raw) + (size_t)groups * slab) + g * n;
+    int *piv = (gws ? reinterpret_cast<int *>(smem_raw)
+                    : reinterpret_cast<int *>(reinterpret_cast<T *>(smem_raw) + (size_t)groups * slab)) + g * n;
     __shared__ T sval[8];
     __shared__ int sidx[8];
     const int nn = n * n;
@@ -263,12 +270,12 @@ gj_generic_kernel(IO io, int n, i64 batch, int *__restrict__ info) {
 // Fused GP mean / variance (see file header).
 template <typename T, int G>
 __global__ void __launch_bounds__(G <= 32 ? 128 : G)
-gp_generic_kernel(GpIO<T> io, int n, i64 batch, int *__restrict__ info) {
+gp_generic_kernel(GpIO<T> io, int n, i64 batch, int *__restrict__ info, T *gws) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int groups = blockDim.x / G;
     const int g = threadIdx.x / G, t = threadIdx.x % G;
     const size_t slab = (size_t)packed_row(n) + 2 * (size_t)n;
-    T *S = reinterpret_cast<T *>(smem_raw) + (size_t)g * slab;
+    T *S = gws ? gws + ((size_t)blockIdx.x * groups + g) * slab : reinterpret_cast<T *>(smem_raw) + (size_t)g * slab;
     __shared__ T scratch[8];
     const int nn = n * n;
 

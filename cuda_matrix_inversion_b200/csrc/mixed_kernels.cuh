@@ -18,13 +18,15 @@ namespace invgpu {
 template <typename T, int G>
 __global__ void __launch_bounds__(G <= 32 ? 256 : G)
 mixed_spd_kernel(const MixedItem *__restrict__ items, i64 count, int nmax, int *__restrict__ info,
-                 unsigned long long *__restrict__ ticket) {
+                 unsigned long long *__restrict__ ticket, T *gws) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ unsigned long long s_unit;
     constexpr int PER_UNIT = (G <= 32) ? 8 : 1;                  // matrices per work unit
     const int g = (G <= 32) ? threadIdx.x / 32 : 0;
     const int t = (G <= 32) ? threadIdx.x % 32 : threadIdx.x;
-    T *S = reinterpret_cast<T *>(smem_raw) + (size_t)g * packed_row(nmax);
+    // gws != null: working copy in a per-CTA slab of global memory (fp64 with nmax > 236 exceeds shared memory)
+    T *S = gws ? gws + ((size_t)blockIdx.x * PER_UNIT + g) * packed_row(nmax)
+               : reinterpret_cast<T *>(smem_raw) + (size_t)g * packed_row(nmax);
 
     for (;;) {
         if (threadIdx.x == 0) s_unit = atomicAdd(ticket, 1ULL);

@@ -220,21 +220,6 @@ int launch_sweep_tma(StridedIO<T> io, i64 batch, int *dInfo, cudaStream_t st, De
     return (int)cudaGetLastError();
 }
 
-// scratch for the (rare) natural-order info recomputation of flagged GP matrices
-static int ensure_gp_scratch(DeviceState *ds, size_t need) {
-    if (ds->gp_scratch_bytes < need) {
-        static std::mutex scratch_mutex;              // not engine_mutex(): the host pipeline holds that one
-        std::lock_guard<std::mutex> lk(scratch_mutex);
-        if (ds->gp_scratch_bytes < need) {
-            if (ds->gp_scratch) cudaFree(ds->gp_scratch);
-            ds->gp_scratch = nullptr; ds->gp_scratch_bytes = 0;
-            INVGPU_TRY(cudaMalloc(&ds->gp_scratch, need));
-            ds->gp_scratch_bytes = need;
-        }
-    }
-    return 0;
-}
-
 template <typename T, int N, int TR, int TC, bool UNROLL, int MINB, int BLK>
 int launch_sweep_gp(GpIO<T> io, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds) {
     using SG = SweepGeo<N, TR, TC>;
@@ -243,9 +228,10 @@ int launch_sweep_gp(GpIO<T> io, i64 batch, int *dInfo, cudaStream_t st, DeviceSt
     int grid = 0;
     int rc = persistent_grid(kern, SG::BLOCK, smem, (batch + SG::MPB - 1) / SG::MPB, ds, &grid);
     if (rc) return rc;
-    rc = ensure_gp_scratch(ds, (size_t)grid * SG::MPB * N * N * sizeof(T));
+    void *scratch = nullptr;
+    rc = ensure_gp_scratch(ds, (size_t)grid * SG::MPB * N * N * sizeof(T), st, &scratch);
     if (rc) return rc;
-    kern<<<grid, SG::BLOCK, smem, st>>>(io, batch, dInfo, (T *)ds->gp_scratch);
+    kern<<<grid, SG::BLOCK, smem, st>>>(io, batch, dInfo, (T *)scratch);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return (int)cudaGetLastError();
 }
@@ -324,9 +310,10 @@ int launch_tile_gp(GpIO<T> io, i64 batch, int *dInfo, cudaStream_t st, DeviceSta
     int grid = 0;
     int rc = persistent_grid(kern, G::BLOCK, smem, (batch + G::MPB - 1) / G::MPB, ds, &grid);
     if (rc) return rc;
-    rc = ensure_gp_scratch(ds, (size_t)grid * G::MPB * N * N * sizeof(T));
+    void *scratch = nullptr;
+    rc = ensure_gp_scratch(ds, (size_t)grid * G::MPB * N * N * sizeof(T), st, &scratch);
     if (rc) return rc;
-    kern<<<grid, G::BLOCK, smem, st>>>(io, batch, dInfo, (T *)ds->gp_scratch);
+    kern<<<grid, G::BLOCK, smem, st>>>(io, batch, dInfo, (T *)scratch);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return (int)cudaGetLastError();
 }

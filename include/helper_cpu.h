@@ -14,6 +14,33 @@
 /* reference include/helper_cpu.h:4 -- size guard of readMatricesFile */
 #define MAX_MATRIX_BYTE_READ 67108864
 
+/* reference include/helper_cpu.h:6-23 -- the error convention of the whole code base: message on stderr, then
+ * exit(EXIT_FAILURE).  `ensure` also reports errno when it is set; callers need <stdio.h>, <stdlib.h>, <errno.h>. */
+#ifndef fail
+#define fail(...)                                           \
+    do {                                                    \
+        fprintf(stderr, "%s:%d\t", __FILE__, __LINE__);     \
+        fprintf(stderr, __VA_ARGS__);                       \
+        fprintf(stderr, "\r\n");                            \
+        exit(EXIT_FAILURE);                                 \
+    } while (0)
+#endif
+#ifndef ensure
+#define ensure(condition, ...)                                                        \
+    do {                                                                              \
+        if (!(condition)) {                                                           \
+            fprintf(stderr, "ENSURE FAILED %s:%d\r\n", __FILE__, __LINE__);           \
+            fprintf(stderr, __VA_ARGS__);                                             \
+            fprintf(stderr, "\r\n");                                                  \
+            if (errno) perror("possible reason for failure from ERRNO");              \
+            exit(EXIT_FAILURE);                                                       \
+        }                                                                             \
+    } while (0)
+#endif
+#ifndef div_ceil
+#define div_ceil(x, y) (1 + (((x) - 1) / (y)))   /* positive x, y */
+#endif
+
 #ifdef __cplusplus
 extern "C" {
 #endif

@@ -29,10 +29,11 @@ extern "C" {
 #define INVGPU_EUNSUPPORTED (-2)   /* n beyond what the selected path supports */
 #define INVGPU_ESINGULAR    (-3)   /* host-flavour call without info[]: some matrix was flagged */
 
+/* largest order every entry point of a family accepts (beyond it: INVGPU_EUNSUPPORTED) */
 #define INVGPU_MAX_N_SPD_F32     256
-#define INVGPU_MAX_N_SPD_F64     128   /* 256 in fp64 does not fit one CTA's shared memory */
-#define INVGPU_MAX_N_GENERAL_F32 128
-#define INVGPU_MAX_N_GENERAL_F64 128
+#define INVGPU_MAX_N_SPD_F64     256
+#define INVGPU_MAX_N_GENERAL_F32 256
+#define INVGPU_MAX_N_GENERAL_F64 256
 
 typedef void *invgpu_stream_t;
 typedef long long invgpu_i64;
@@ -110,6 +111,14 @@ int invgpu_gp_host_f32(int n, const float *As, const float *Bs, const float *Cs,
                        float *Means, float *Variances, invgpu_i64 batch, int *info);
 int invgpu_gp_host_f64(int n, const double *As, const double *Bs, const double *Cs, const double *Ds, const double *Es,
                        double *Means, double *Variances, invgpu_i64 batch, int *info);
+
+/* Transfer probe: the host pipeline above with the kernel replaced by a device-to-device copy -- `batch` units of
+ * `unit_bytes` go host -> device -> host through the same chunks, streams and ring.  What it measures is the
+ * ceiling of every host-flavour call on this box (bench.py `e2e_ceiling`, tools/xfer_bench); it is the engine's
+ * counterpart of the reference's transfer micro-benchmarks (src/bench.cu:26-158). */
+int invgpu_xfer_roundtrip_host(const void *in, void *out, unsigned long long unit_bytes, invgpu_i64 batch);
+/* NUMA node of a CUDA device (sysfs), -1 when the platform does not say. */
+int invgpu_device_numa_node(int device);
 
 /* pinned host allocations for callers that want the zero-staging fast path of the host flavour */
 void *invgpu_host_alloc(unsigned long long bytes);

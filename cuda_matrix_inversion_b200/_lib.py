@@ -42,6 +42,11 @@ def _load() -> C.CDLL:
         sig[f"invgpu_spd_stages_ptrs_{sfx}"] = (_int, [_vp, _vp, _int, _int, _int, _vp, _vp])
         sig[f"invgpu_general_inverse_ptrs_{sfx}"] = (_int, [_vp, _vp, _int, _int, _vp, _vp])
         sig[f"invgpu_mixed_spd_inverse_{sfx}"] = (_int, [_vp, _vp, _vp, _i64, _vp, _vp])
+        sig[f"invgpu_getrf_{sfx}"] = (_int, [_vp, _int, _vp, _vp, _i64, _vp])
+        sig[f"invgpu_getrf_ptrs_{sfx}"] = (_int, [_vp, _int, _vp, _vp, _int, _vp])
+        sig[f"invgpu_getri_{sfx}"] = (_int, [_vp, _vp, _vp, _int, _vp, _i64, _vp])
+        sig[f"invgpu_getri_ptrs_{sfx}"] = (_int, [_vp, _vp, _vp, _int, _vp, _int, _vp])
+        sig[f"invgpu_gesv_{sfx}"] = (_int, [_vp, _vp, _vp, _int, _int, _vp, _i64, _vp])
         sig[f"invgpu_gp_{sfx}"] = (_int, [_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp])
         sig[f"invgpu_spd_inverse_host_{sfx}"] = (_int, [_vp, _vp, _int, _i64, _vp])
         sig[f"invgpu_general_inverse_host_{sfx}"] = (_int, [_vp, _vp, _int, _i64, _vp])

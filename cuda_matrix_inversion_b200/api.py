@@ -160,6 +160,24 @@ def gp_device(n: int, dA: int, dB: int, dC: int, dD: int, dE: int, d_means: int,
               stream or None), "gp_device")
 
 
+def getrf_device(dA: int, n: int, batch: int, dtype, d_pivots: int = 0, d_info: int = 0, stream: int = 0) -> None:
+    """P A = L U in place with 1-based pivots and sgetrf info (cublasSgetrfBatched semantics)."""
+    fn = getattr(lib, "invgpu_getrf_" + _sfx(dtype))
+    _check(fn(dA, n, d_pivots or None, d_info or None, batch, stream or None), "getrf_device")
+
+
+def getri_device(dLU: int, d_pivots: int, dAinv: int, n: int, batch: int, dtype, d_info: int = 0, stream: int = 0) -> None:
+    fn = getattr(lib, "invgpu_getri_" + _sfx(dtype))
+    _check(fn(dLU, d_pivots, dAinv, n, d_info or None, batch, stream or None), "getri_device")
+
+
+def gesv_device(dA: int, dB: int, n: int, nrhs: int, batch: int, dtype, d_pivots: int = 0, d_info: int = 0,
+                stream: int = 0) -> None:
+    """Solve A X = B for nrhs right-hand sides per matrix: A := LU, B := X."""
+    fn = getattr(lib, "invgpu_gesv_" + _sfx(dtype))
+    _check(fn(dA, d_pivots or None, dB, n, nrhs, d_info or None, batch, stream or None), "gesv_device")
+
+
 def spd_stages_ptrs_device(d_ptrs_in: int, d_ptrs_out: int, n: int, batch: int, stages: int, dtype,
                            d_info: int = 0, stream: int = 0) -> None:
     fn = getattr(lib, "invgpu_spd_stages_ptrs_" + _sfx(dtype))

@@ -10,6 +10,7 @@
  *                   and time it for the *_cpu rows.  Without it those rows are omitted: this
  *                   program has no CPU implementation of its own.
  *   --json          one extra JSON line with throughput and the roofline fraction
+ *   --dump PATH     write the raw output array of the last algorithm (tests compare runs bit for bit)
  */
 #ifndef INVGPU_BENCH_COMMON_H
 #define INVGPU_BENCH_COMMON_H
@@ -79,16 +80,18 @@ typedef struct {
     bool csv, json;
     int gpus;
     const char *cpu_lib;
+    const char *dump;
 } bench_opts;
 
 static inline bench_opts parse_opts(int argc, char const *argv[])
 {
-    bench_opts o = {false, false, 1, NULL};
+    bench_opts o = {false, false, 1, NULL, NULL};
     for (int i = 4; i < argc; ++i) {
         if (!strncmp("-csv", argv[i], 4)) o.csv = true;
         else if (!strcmp("--json", argv[i])) o.json = true;
         else if (!strcmp("--gpus", argv[i]) && i + 1 < argc) o.gpus = atoi(argv[++i]);
         else if (!strcmp("--cpu-lib", argv[i]) && i + 1 < argc) o.cpu_lib = argv[++i];
+        else if (!strcmp("--dump", argv[i]) && i + 1 < argc) o.dump = argv[++i];
     }
     if (o.gpus < 1) o.gpus = 1;
     return o;

@@ -8,6 +8,7 @@
 #include "generic_smem.cuh"
 #include "fast_tiers.cuh"
 #include "mixed_kernels.cuh"
+#include "lu_kernels.cuh"
 #include <chrono>
 #include <atomic>
 #include <vector>
@@ -132,6 +133,35 @@ static int run_gp(GpIO<T> io, int n, i64 batch, int *dInfo, cudaStream_t st) {
     return INVGPU_EUNSUPPORTED;
 }
 
+// LU factors / inverse from factors / multi-RHS solve (lu_kernels.cuh)
+template <typename T, typename IO>
+static int run_getrf(IO io, int n, i64 batch, int *dPivots, int *dInfo, T *dB, int nrhs, cudaStream_t st) {
+    if (n < 1 || batch < 0 || nrhs < 0 || (nrhs > 0 && !dB)) return INVGPU_EARG;
+    if (n > 256 || nrhs > 256) return INVGPU_EUNSUPPORTED;
+    if (batch == 0) return 0;
+    int err = 0;
+    DeviceState *ds = device_state(&err);
+    if (!ds) return err;
+    const size_t slab = (size_t)n * ((n + nrhs) | 1) * sizeof(T), piv = (size_t)n * sizeof(int);
+    if (n <= 32) return launch_generic<T>(lu_factor_kernel<T, 32, IO>, 128, slab, 4 * piv, 4, batch, ds, st, io, n, batch, dPivots, dInfo, dB, nrhs);
+    if (n <= 128) return launch_generic<T>(lu_factor_kernel<T, 128, IO>, 128, slab, piv, 1, batch, ds, st, io, n, batch, dPivots, dInfo, dB, nrhs);
+    return launch_generic<T>(lu_factor_kernel<T, 256, IO>, 256, slab, piv, 1, batch, ds, st, io, n, batch, dPivots, dInfo, dB, nrhs);
+}
+
+template <typename T, typename IO>
+static int run_getri(IO io, int n, i64 batch, const int *dPivots, int *dInfo, cudaStream_t st) {
+    if (n < 1 || batch < 0 || !dPivots) return INVGPU_EARG;
+    if (n > 256) return INVGPU_EUNSUPPORTED;
+    if (batch == 0) return 0;
+    int err = 0;
+    DeviceState *ds = device_state(&err);
+    if (!ds) return err;
+    const size_t slab = ((size_t)n * (n | 1) + n) * sizeof(T), piv = (size_t)n * sizeof(int);
+    if (n <= 32) return launch_generic<T>(lu_invert_kernel<T, 32, IO>, 128, slab, 4 * piv, 4, batch, ds, st, io, n, batch, dPivots, dInfo);
+    if (n <= 128) return launch_generic<T>(lu_invert_kernel<T, 128, IO>, 128, slab, piv, 1, batch, ds, st, io, n, batch, dPivots, dInfo);
+    return launch_generic<T>(lu_invert_kernel<T, 256, IO>, 256, slab, piv, 1, batch, ds, st, io, n, batch, dPivots, dInfo);
+}
+
 template <typename T>
 static StridedIO<T> dense_io(const T *in, T *out, int n) {
     StridedIO<T> io;
@@ -216,6 +246,30 @@ static int ensure_pipeline(DeviceState *ds, size_t slot_bytes, size_t ring_bytes
 
 static size_t g_chunk_bytes = 0;   // 0 = default; settable through INVGPU_CHUNK_MB
 
+// Staging copy of a pageable user buffer into / out of the pinned ring.  One host thread moves ~9 GB/s on the
+// B200 boxes' hosts (profiles/r2_xfer_n1.csv: pageable pipeline 8.7 GB/s vs 87 GB/s pinned), so large copies are
+// split over a few threads (INVGPU_STAGE_THREADS, default 4; 1 = off).
+static void staging_copy(void *dst, const void *src, size_t bytes) {
+    static int nthr = -1;
+    if (nthr < 0) {
+        const char *e = getenv("INVGPU_STAGE_THREADS");
+        nthr = e ? atoi(e) : 4;
+        const int hw = (int)std::thread::hardware_concurrency();
+        if (hw > 0 && nthr > hw) nthr = hw;
+        if (nthr < 1) nthr = 1;
+    }
+    if (nthr == 1 || bytes < ((size_t)2 << 20)) { memcpy(dst, src, bytes); return; }
+    const size_t part = ((bytes / nthr) + 4095) & ~(size_t)4095;
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nthr; ++t) {
+        const size_t off = (size_t)t * part;
+        if (off >= bytes) break;
+        pool.emplace_back([=] { memcpy((char *)dst + off, (const char *)src + off, std::min(part, bytes - off)); });
+    }
+    memcpy(dst, src, std::min(part, bytes));
+    for (auto &th : pool) th.join();
+}
+
 // Phase timers of the reference's `make log=1` build (-DDETAILED_LOGGING; include/timer.h:8-9 and e.g.
 // src/gauss/batched_invert.cu:114-171): every *_gpu wrapper prints "<name>_mem_htod / _ker / _mem_dtoh,batch,n,ms,ns".
 // Here the three phases overlap chunk by chunk, so what is reported per phase is the BUSY time of its stream
@@ -298,7 +352,7 @@ static int host_pipeline(std::vector<HostArr> &arrs, i64 batch, int *info, int *
                     if (info) info[first + i] = ci[i];
                 }
             } else if (!a.pinned && a.out) {
-                memcpy(a.out + (size_t)first * a.unit, ring, (size_t)cnt * a.unit);
+                staging_copy(a.out + (size_t)first * a.unit, ring, (size_t)cnt * a.unit);
             }
         }
         return 0;
@@ -326,7 +380,7 @@ static int host_pipeline(std::vector<HostArr> &arrs, i64 batch, int *info, int *
         for (auto &a : arrs) {
             if (!a.in) continue;
             const char *src = a.in + (size_t)first * a.unit;
-            if (!a.pinned) { memcpy(hbase + a.off, src, (size_t)cnt * a.unit); src = hbase + a.off; }
+            if (!a.pinned) { staging_copy(hbase + a.off, src, (size_t)cnt * a.unit); src = hbase + a.off; }
             INVGPU_PIPE_TRY(cudaMemcpyAsync(dbase + a.off, src, (size_t)cnt * a.unit, cudaMemcpyHostToDevice, ds->s_in));
         }
         stamp(ds->s_in);
@@ -638,6 +692,32 @@ int invgpu_general_inverse_ptrs_f64(double *const *As, double *const *Ainvs, int
     return run_general<double, PtrIO<double>>(io, n, batch, dInfo, (cudaStream_t)s);
 }
 
+#define INVGPU_LU_ENTRY(SFX, T)                                                                                       \
+    int invgpu_getrf_##SFX(T *dA, int n, int *dPivots, int *dInfo, invgpu_i64 batch, invgpu_stream_t s) {              \
+        if (!dA) return INVGPU_EARG;                                                                                   \
+        return run_getrf<T, StridedIO<T>>(dense_io<T>(dA, dA, n), n, batch, dPivots, dInfo, nullptr, 0, (cudaStream_t)s); \
+    }                                                                                                                  \
+    int invgpu_getrf_ptrs_##SFX(T *const *As, int n, int *dPivots, int *dInfo, int batch, invgpu_stream_t s) {         \
+        if (!As) return INVGPU_EARG;                                                                                   \
+        PtrIO<T> io; io.in = As; io.out = As;                                                                          \
+        return run_getrf<T, PtrIO<T>>(io, n, batch, dPivots, dInfo, nullptr, 0, (cudaStream_t)s);                      \
+    }                                                                                                                  \
+    int invgpu_getri_##SFX(const T *dLU, const int *dPivots, T *dAinv, int n, int *dInfo, invgpu_i64 batch, invgpu_stream_t s) { \
+        if (!dLU || !dAinv) return INVGPU_EARG;                                                                        \
+        return run_getri<T, StridedIO<T>>(dense_io<T>(dLU, dAinv, n), n, batch, dPivots, dInfo, (cudaStream_t)s);      \
+    }                                                                                                                  \
+    int invgpu_getri_ptrs_##SFX(T *const *LUs, const int *dPivots, T *const *Ainvs, int n, int *dInfo, int batch, invgpu_stream_t s) { \
+        if (!LUs || !Ainvs) return INVGPU_EARG;                                                                        \
+        PtrIO<T> io; io.in = LUs; io.out = Ainvs;                                                                      \
+        return run_getri<T, PtrIO<T>>(io, n, batch, dPivots, dInfo, (cudaStream_t)s);                                  \
+    }                                                                                                                  \
+    int invgpu_gesv_##SFX(T *dA, int *dPivots, T *dB, int n, int nrhs, int *dInfo, invgpu_i64 batch, invgpu_stream_t s) { \
+        if (!dA || !dB || nrhs < 1) return INVGPU_EARG;                                                                \
+        return run_getrf<T, StridedIO<T>>(dense_io<T>(dA, dA, n), n, batch, dPivots, dInfo, dB, nrhs, (cudaStream_t)s); \
+    }
+INVGPU_LU_ENTRY(f32, float)
+INVGPU_LU_ENTRY(f64, double)
+
 int invgpu_gp_f32(int n, const float *dA, const float *dB, const float *dC, const float *dD, const float *dE,
                   float *dMeans, float *dVariances, invgpu_i64 batch, int *dInfo, invgpu_stream_t s) {
     GpIO<float> io{dA, dB, dC, dD, dE, dMeans, dVariances};
@@ -807,9 +887,19 @@ void inverse_gauss_batched_device(cublasHandle_t, int N, Array *devAs, Array *de
     int rc = invgpu_general_inverse_ptrs_f32(devAs, devAInvs, N, batchSize, nullptr, nullptr);
     legacy_check(rc, "inverse_gauss_batched_device", nullptr, kLuMsg);
 }
+// Upstream (src/gauss/inverse_gpu.cu:16-58) this is cublasSgetrfBatched IN PLACE on devAs followed by getriBatched
+// into devAInvs: the caller finds the LU factors in devAs afterwards.  Here the inverse comes from the fast
+// Gauss-Jordan tiers (it reads devAs first), then devAs is factored in place so that the side effect is the
+// same (INVGPU_LEGACY_LU_FACTORS=0 skips that second kernel; aliased in/out arrays skip it too).
 void inverse_lu_cuda_batched_device(cublasHandle_t, int N, Array *devAs, Array *devAInvs, int batchSize) {
     int rc = invgpu_general_inverse_ptrs_f32(devAs, devAInvs, N, batchSize, nullptr, nullptr);
     legacy_check(rc, "inverse_lu_cuda_batched_device", nullptr, kLuMsg);
+    static int leave_lu = -1;
+    if (leave_lu < 0) { const char *e = getenv("INVGPU_LEGACY_LU_FACTORS"); leave_lu = (e && !strcmp(e, "0")) ? 0 : 1; }
+    if (leave_lu && devAs != devAInvs && N <= 256) {
+        rc = invgpu_getrf_ptrs_f32(devAs, N, nullptr, nullptr, batchSize, nullptr);
+        legacy_check(rc, "inverse_lu_cuda_batched_device (LU factors)", nullptr, kLuMsg);
+    }
 }
 
 // reference src/helper.cu:103-118: ONE pitched allocation for the batch, per-matrix pointers into a host array

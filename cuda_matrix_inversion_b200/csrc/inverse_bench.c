@@ -122,6 +122,11 @@ int main(int argc, char const *argv[])
         printf("{\"bench\": \"inverse_bench\", \"n\": %d, \"numMatrices\": %d, \"gpus\": %d, \"best_ms\": %.6f, "
                "\"inversions_per_s\": %.6e, \"end_to_end\": true}\n",
                n, numMatrices, opt.gpus, best_ms, numMatrices / (best_ms * 1e-3));
+    if (opt.dump) {
+        FILE *f = fopen(opt.dump, "wb");
+        BENCH_ENSURE(f && fwrite(inv, sizeof(float), total, f) == total, "could not write %s", opt.dump);
+        fclose(f);
+    }
     free(work); free(inv); free(a); free(aInv);
     return 0;
 }

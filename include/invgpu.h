@@ -68,6 +68,26 @@ int invgpu_spd_factor_f64(const double *dA, double *dL, int n, invgpu_i64 batch,
 int invgpu_general_inverse_f32(const float *dA, float *dAinv, int n, invgpu_i64 batch, int *dInfo, invgpu_stream_t stream);
 int invgpu_general_inverse_f64(const double *dA, double *dAinv, int n, invgpu_i64 batch, int *dInfo, invgpu_stream_t stream);
 
+/* ---- LU factors with pivots / inverse from factors / multi-RHS solve ------------------------ *
+ * The cublasSgetrfBatched / cublasSgetriBatched pair of the reference's fastest GPU path
+ * (src/gauss/inverse_gpu.cu:24-33 getrf in place with PivotArray / infoArray :21-22, :39-50 getri out of place)
+ * for callers that want the FACTORS, and the solve its CPU side formulates with spotrs_ (src/gauss_cpu.c:87-144),
+ * generalised to non-symmetric systems.  LAPACK semantics: P A = L U in place (unit lower L, U), dPivots[k*n + i] =
+ * 1-based row that row i was interchanged with, dInfo[k] = first i with U(i,i) exactly zero (the factorisation is
+ * completed anyway; getri / gesv then give NaN for that matrix).  dPivots / dInfo are DEVICE arrays, may be NULL
+ * in getrf / gesv.  n <= 256, nrhs <= 256.  B is n x nrhs column-major (ldb = n), batch dense; gesv leaves LU in dA
+ * and X in dB.  `_ptrs`: cuBLAS-style arrays of per-matrix device pointers (lda = n). */
+int invgpu_getrf_f32(float *dA, int n, int *dPivots, int *dInfo, invgpu_i64 batch, invgpu_stream_t stream);
+int invgpu_getrf_f64(double *dA, int n, int *dPivots, int *dInfo, invgpu_i64 batch, invgpu_stream_t stream);
+int invgpu_getrf_ptrs_f32(float *const *As, int n, int *dPivots, int *dInfo, int batch, invgpu_stream_t stream);
+int invgpu_getrf_ptrs_f64(double *const *As, int n, int *dPivots, int *dInfo, int batch, invgpu_stream_t stream);
+int invgpu_getri_f32(const float *dLU, const int *dPivots, float *dAinv, int n, int *dInfo, invgpu_i64 batch, invgpu_stream_t stream);
+int invgpu_getri_f64(const double *dLU, const int *dPivots, double *dAinv, int n, int *dInfo, invgpu_i64 batch, invgpu_stream_t stream);
+int invgpu_getri_ptrs_f32(float *const *LUs, const int *dPivots, float *const *Ainvs, int n, int *dInfo, int batch, invgpu_stream_t stream);
+int invgpu_getri_ptrs_f64(double *const *LUs, const int *dPivots, double *const *Ainvs, int n, int *dInfo, int batch, invgpu_stream_t stream);
+int invgpu_gesv_f32(float *dA, int *dPivots, float *dB, int n, int nrhs, int *dInfo, invgpu_i64 batch, invgpu_stream_t stream);
+int invgpu_gesv_f64(double *dA, int *dPivots, double *dB, int n, int nrhs, int *dInfo, invgpu_i64 batch, invgpu_stream_t stream);
+
 /* ---- pointer-array flavour (reference `Array *devAs`) ------------------------------------ *
  * As[k] / Ainvs[k] are device pointers; the arrays may be in pinned-host or device memory.
  * stages: bit mask 1 = potrf, 2 = trtri, 4 = lauum (7 = full inverse, 1 = factor);

@@ -156,6 +156,26 @@ def lu_inverse(flat: np.ndarray, n: int):
     return out, info
 
 
+def getrf(flat: np.ndarray, n: int):
+    """LU factors of every matrix (LAPACK sgetf2 semantics) -> (lu_flat, ipiv[batch, n] 1-based, info[batch])."""
+    lu = np.ascontiguousarray(flat).copy()
+    batch = lu.size // (n * n)
+    ipiv = np.zeros((batch, n), dtype=np.int32)
+    info = np.zeros(batch, dtype=np.int32)
+    fn = getattr(lib(), "orc_getrf_batch_" + _suffix(lu.dtype))
+    fn(_p(lu), C.c_int(n), C.c_long(batch), _p(ipiv), _p(info))
+    return lu, ipiv, info
+
+
+def getrs(lu: np.ndarray, ipiv: np.ndarray, b: np.ndarray, n: int, nrhs: int) -> np.ndarray:
+    """Solve with the factors (sgetrs 'N'); b is batch x (n x nrhs column-major)."""
+    x = np.ascontiguousarray(b).copy()
+    batch = lu.size // (n * n)
+    fn = getattr(lib(), "orc_getrs_batch_" + _suffix(lu.dtype))
+    fn(_p(np.ascontiguousarray(lu)), _p(np.ascontiguousarray(ipiv, dtype=np.int32)), _p(x), C.c_int(n), C.c_int(nrhs), C.c_long(batch))
+    return x
+
+
 def _gp(which, n, a, b, c, x):
     a, b, c, x = (np.ascontiguousarray(v) for v in (a, b, c, x))
     batch = b.size // (n * n)

@@ -22,7 +22,11 @@ def _declared_symbols():
     for hdr in ("gauss_gpu.h", "helper_cpu.h", "invgpu.h"):
         src = open(os.path.join(INCLUDE, hdr)).read()
         src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        src = re.sub(r"^[ \t]*#[ \t]*define(?:\\\n|[^\n])*", "", src, flags=re.M)     # macro bodies (fail / ensure / div_ceil)
         names |= set(re.findall(r"\b(\w+)\s*\([^;{]*\)\s*;", src))
+    # helper_gpu.h needs <cuda_runtime.h>: its one exported function is listed by name
+    assert "batchedCudaMalloc(" in open(os.path.join(INCLUDE, "helper_gpu.h")).read()
+    names.add("batchedCudaMalloc")
     return names - {"defined"}
 
 
@@ -50,6 +54,17 @@ def test_headers_compile_as_c_and_cxx(tmp_path):
                    '#include "invgpu.h"\nint main(void){return 0;}\n')
     subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", INCLUDE, "-c", str(src), "-o", str(tmp_path / "t.o")], check=True)
     subprocess.run(["g++", "-x", "c++", "-Wall", "-Werror", "-I", INCLUDE, "-c", str(src), "-o", str(tmp_path / "t2.o")], check=True)
+    # the reference's include order (src/gauss_bench.cu:6-18): cuda_runtime.h, cublas_v2.h, types.h, helper_cpu.h, helper_gpu.h
+    cuda_inc = "/usr/local/cuda/include"
+    if os.path.exists(os.path.join(cuda_inc, "cublas_v2.h")):
+        src2 = tmp_path / "u.c"
+        src2.write_text('#include <stdio.h>\n#include <stdlib.h>\n#include <errno.h>\n#include <cuda_runtime.h>\n#include "cublas_v2.h"\n'
+                        '#include "types.h"\n#include "helper_cpu.h"\n#include "helper_gpu.h"\n#include "inverse_gpu.h"\n'
+                        'int main(void){ size_t p; Array d[2]; gpuErrchk(batchedCudaMalloc(d, &p, 64, 2)); cublasErrchk(CUBLAS_STATUS_SUCCESS);\n'
+                        ' ensure(div_ceil(5, 2) == 3, "div_ceil"); if (p == 1) { fail("unreachable %d", 1); } return 0; }\n')
+        for cc, extra in (("gcc", ["-std=gnu99"]), ("g++", ["-x", "c++"])):
+            subprocess.run([cc, *extra, "-Wall", "-Werror", "-Wno-unused-function", "-I", INCLUDE, "-I", cuda_inc, "-c", str(src2),
+                            "-o", str(tmp_path / "u.o")], check=True)
 
 
 def test_ctypes_mirror_binds_everything():

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 import oracle as orc
-from tests.util import (TOL, general_batch, gp_batch, load_fixture, normwise_err, residual_inf, spd_batch)
+from tests.util import (TOL, assert_general_parity, general_batch, gp_batch, load_fixture, normwise_err, residual_inf, spd_batch)
 
 pytestmark = pytest.mark.gpu
 
@@ -179,15 +179,9 @@ def test_general_inverse_reference_fixtures(api, fixtures_dir, n, dtype):
     want, oinfo = orc.gauss_jordan_inverse(flat, n)
     assert not info.any() and not oinfo.any()
     got3, want3 = orc.from_colmajor(got, n), orc.from_colmajor(want, n)
-    exact = np.linalg.inv(a.astype(np.float64))
-    cond = np.linalg.cond(a.astype(np.float64)).max()
-    eps = np.finfo(dtype).eps
-    # these fixtures have cond up to 9e3: the stated tolerance applies where cond*eps allows it,
-    # and in every case the CUDA result must be as close to the truth as the oracle's is.
-    bound = max(TOL[np.dtype(dtype)], 16 * eps * cond)
-    assert normwise_err(got3, exact) <= bound
-    assert normwise_err(got3, want3) <= bound
-    assert residual_inf(a, got3) <= max(TOL[np.dtype(dtype)], 64 * eps * cond)
+    # cond up to 9e3 here; the tolerance is nevertheless asserted outright (tests/util.py::assert_general_parity)
+    e_gpu, _ = assert_general_parity(a, got3, want3, dtype, f"square_5_{n}")
+    assert e_gpu <= TOL[np.dtype(dtype)]
 
 
 def test_general_inverse_square_100_64_64_regenerated(api, golden_dir):
@@ -197,20 +191,22 @@ def test_general_inverse_square_100_64_64_regenerated(api, golden_dir):
     a = np.load(p)["a"]                         # [100, 64, 64] float32
     from tests.golden.make_square_100_64_64 import generate
     np.testing.assert_array_equal(a, generate())       # the committed fixture is what the script makes
-    inv64 = np.linalg.inv(a.astype(np.float64))
-    cond = np.linalg.cond(a.astype(np.float64))
     flat = orc.to_colmajor(a)
     got, info = api.general_inverse_host(flat, 64)
     assert not info.any()
     got3 = orc.from_colmajor(got, 64)
-    err = np.abs(got3 - inv64).reshape(100, -1).max(1) / np.abs(inv64).reshape(100, -1).max(1)
-    assert (err <= np.maximum(1e-4, 16 * np.finfo(np.float32).eps * cond)).all()
     want, _ = orc.gauss_jordan_inverse(flat, 64)
     want3 = orc.from_colmajor(want, 64)
-    dev = np.abs(got3 - want3).reshape(100, -1).max(1) / np.abs(want3).reshape(100, -1).max(1)
-    assert (dev <= np.maximum(1e-4, 16 * np.finfo(np.float32).eps * cond)).all()   # cond of U(0,1) 64x64: 1e2..1e4
-    res = np.abs(a.astype(np.float64) @ got3.astype(np.float64) - np.eye(64)).sum(-1).max(-1)
-    assert (res <= np.maximum(1e-4, 64 * np.finfo(np.float32).eps * cond)).all()
+    # per matrix (cond of U(0,1) 64x64 ranges 1e2..1e5): error vs the fp64 truth within 1e-4 or 4x the oracle's own
+    inv64 = np.linalg.inv(a.astype(np.float64))
+    den = np.abs(inv64).reshape(100, -1).max(1)
+    e_gpu = np.abs(got3 - inv64).reshape(100, -1).max(1) / den
+    e_orc = np.abs(want3 - inv64).reshape(100, -1).max(1) / den
+    print(f"[parity square_100_64_64] gpu err max {e_gpu.max():.2e} median {np.median(e_gpu):.2e}; oracle max {e_orc.max():.2e}")
+    assert (e_gpu <= np.maximum(1e-4, 4 * e_orc)).all()
+    assert np.median(e_gpu) <= 1e-4
+    res = lambda x: np.abs(a.astype(np.float64) @ x.astype(np.float64) - np.eye(64)).sum(-1).max(-1)
+    assert (res(got3) <= np.maximum(1e-4, 4 * res(want3))).all()
 
 
 @pytest.mark.parametrize("n", [1, 2, 3, 7, 13, 31, 33, 50, 100])
@@ -226,10 +222,7 @@ def test_general_inverse_sizes(api, n, dtype):
     want, oinfo = orc.gauss_jordan_inverse(flat, n)
     np.testing.assert_array_equal(info, oinfo)
     assert not info.any()
-    cond = np.linalg.cond(a.astype(np.float64)).max()
-    bound = max(TOL[np.dtype(dtype)], 16 * np.finfo(dtype).eps * cond)
-    assert normwise_err(orc.from_colmajor(got, n), orc.from_colmajor(want, n)) <= bound
-    assert residual_inf(a, orc.from_colmajor(got, n)) <= 4 * bound
+    assert_general_parity(a, orc.from_colmajor(got, n), orc.from_colmajor(want, n), dtype, f"sizes n={n}")
 
 
 @pytest.mark.parametrize("n", [6, 8])                           # 8: the thread-per-matrix kernel (explicit row swaps)
@@ -274,8 +267,7 @@ def test_general_flags_tile_tiers(api, n, dtype):
     np.testing.assert_array_equal(info, oinfo)
     assert info[1] == n // 2 + 1 and info[3] == 1 and info[4] == n and (info != 0).sum() == 3
     good = info == 0
-    tol = max(TOL[np.dtype(dtype)], 16 * np.finfo(dtype).eps * 1e3)
-    assert normwise_err(orc.from_colmajor(got, n)[good], orc.from_colmajor(want, n)[good]) <= tol
+    assert_general_parity(a[good], orc.from_colmajor(got, n)[good], orc.from_colmajor(want, n)[good], dtype, f"flags n={n}")
     assert np.isnan(orc.from_colmajor(got, n)[~good]).all()
     want_tier = "warp-rowlane" if (dtype == np.float32 and n <= 64) else "gj-tile"
     assert api.tier_name("general", n, dtype).startswith(want_tier)
@@ -411,6 +403,9 @@ def test_legacy_device_entry_points(api, torch, ptrs_on):
         d_o.zero_()
         getattr(lib, name)(None, n, pa.data_ptr(), po.data_ptr(), batch)
         assert normwise_err(out(), want) <= 1e-4, name
+    # inverse_lu_cuda_batched_device leaves the LU factors in devAs like upstream (cublasSgetrfBatched in place,
+    # src/gauss/inverse_gpu.cu:24-33): restore the input for the calls below
+    d_a.view(batch, pitch // 4)[:, : n * n] = torch.from_numpy(orc.to_colmajor(a)).view(batch, n * n).cuda()
     # stride family: in place on devAInvs, staged == fused
     d_o.copy_(d_a)
     lib.decompose_cholesky_stride_batched_device(None, n, pa.data_ptr(), po.data_ptr(), batch)

@@ -202,3 +202,38 @@ def test_flags_match_lapack_semantics(fixtures_dir):
         _, info = orc.chol_inverse(orc.to_colmajor(s[None]), n)
         _, li = sl.lapack.dpotrf(s, lower=0)
         assert info[0] == li
+
+
+# --------------------------------------------------------------------------------------- LU factors / solve (section 8 f4)
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("n", [1, 2, 5, 16, 33, 64])
+def test_getrf_matches_lapack_pivots_and_factors(n, dtype):
+    """orc_getrf (sgetf2 restated) against LAPACK getrf through scipy: pivot indices bit-exact, factors to rounding,
+    and getrs against numpy's fp64 solve -- this is what pins the GPU getrf / gesv tests."""
+    import scipy.linalg as sl
+    rng = np.random.default_rng(n)
+    a = rng.random((9, n, n)).astype(dtype)
+    lu, ipiv, info = orc.getrf(orc.to_colmajor(a), n)
+    assert not info.any() and ipiv.min() >= 1 and ipiv.max() <= n
+    lu3 = orc.from_colmajor(lu, n)
+    tol = 2e-4 if dtype == np.float32 else 1e-11
+    for k in range(9):
+        lu_s, piv_s = sl.lu_factor(a[k])
+        np.testing.assert_array_equal(piv_s + 1, ipiv[k])
+        assert np.abs(lu3[k] - lu_s).max() <= tol * max(1.0, np.abs(lu_s).max())
+    b = rng.random((9, 3, n)).astype(dtype)                       # three right-hand sides, column-major n x 3
+    x = orc.getrs(lu, ipiv, b.reshape(-1), n, 3).reshape(9, 3, n)
+    want = np.linalg.solve(a.astype(np.float64), b.transpose(0, 2, 1).astype(np.float64)).transpose(0, 2, 1)
+    cond = np.linalg.cond(a.astype(np.float64)).max()
+    assert np.abs(x - want).max() <= 8 * np.finfo(dtype).eps * cond * max(1.0, np.abs(want).max())
+
+
+def test_getrf_zero_pivot_info_and_completion():
+    """sgetf2 semantics: an exactly-zero pivot column is recorded (info = first k) and the factorisation goes on."""
+    import scipy.linalg as sl
+    a = np.array([[[1.0, 2.0, 3.0], [2.0, 4.0, 6.0], [1.0, 1.0, 1.0]]])     # rank 2, a zero pivot appears at step 3
+    lu, ipiv, info = orc.getrf(orc.to_colmajor(a), 3)
+    lu_s, piv_s = sl.lu_factor(a[0], check_finite=False)
+    np.testing.assert_array_equal(piv_s + 1, ipiv[0])
+    assert info[0] == 3
+    np.testing.assert_allclose(orc.from_colmajor(lu, 3)[0], lu_s, atol=1e-15)

@@ -50,3 +50,24 @@ def normwise_err(got, want):
     num = np.abs(got - want).reshape(got.shape[0], -1).max(axis=1)
     den = np.abs(want).reshape(want.shape[0], -1).max(axis=1)
     return (num / den).max()
+
+
+def assert_general_parity(a, got3, want3, dtype, label=""):
+    """The bar for general (non-symmetric) inverses, printed into the test log:
+      * normwise error of the CUDA result against the fp64 truth <= the north_star tolerance (1e-4 / 1e-10)
+        OUTRIGHT -- no cond-scaled slack (the fp32 oracle reaches 6e-7..1.5e-5 on the reference's square_5_*
+        fixtures, cond <= 9e3) -- and never worse than 4x the oracle's own error where that is larger;
+      * normwise deviation from the oracle <= the same tolerance;
+      * residual ||A A^-1 - I||_inf <= max(tolerance, 4 x the oracle's own residual): only the residual
+        legitimately exceeds 1e-4 at cond ~1e4 in fp32 (oracle: 3e-4..8e-4)."""
+    tol = TOL[np.dtype(dtype)]
+    exact = np.linalg.inv(np.asarray(a, dtype=np.float64))
+    e_gpu, e_orc = normwise_err(got3, exact), normwise_err(want3, exact)
+    dev = normwise_err(got3, want3)
+    r_gpu, r_orc = residual_inf(a, got3), residual_inf(a, want3)
+    print(f"[parity {label} {np.dtype(dtype).name}] err vs fp64 truth: gpu {e_gpu:.2e} oracle {e_orc:.2e}; "
+          f"gpu vs oracle {dev:.2e}; residual: gpu {r_gpu:.2e} oracle {r_orc:.2e}")
+    assert e_gpu <= max(tol, 4 * e_orc), (e_gpu, e_orc)
+    assert dev <= max(tol, 4 * e_orc), (dev, e_orc)
+    assert r_gpu <= max(tol, 4 * r_orc), (r_gpu, r_orc)
+    return e_gpu, e_orc

@@ -15,13 +15,19 @@ One JSON line on stdout (rank 0):
             max over ranks); inputs (4.3 GB) and outputs (4.3 GB) are far larger than the 126 MB L2
   e2e       the same metric through the reference-facing host call (invgpu_spd_inverse_host_f32 ==
             inverse_cholesky_batched_gpu without the abort), pinned HOST buffers in, HOST buffers
-            out, H2D + D2H inside the timed region
+            out, H2D + D2H inside the timed region; `ceiling` / `e2e_ceiling` = the same pipeline with the
+            kernel replaced by a device copy (copy-only: what the box's host<->device path allows with all
+            ranks transferring at once), `frac_of_ceiling` = e2e / ceiling
   roofline  algorithmic bytes (2 n^2 sizeof(T) per matrix) / measured kernel time vs the measured
             HBM copy peak in MEASURED_PEAKS.json
   cpu_baseline  the reference's own CPU path (oracle/_ref: inverse_chol_blas_omp, src/inverse.c:100,
             OpenBLAS 0.3.15) on a bounded sample, all host cores
-  extra     the other BASELINE configs that fit one GPU (n sweep, fp64, Gauss-Jordan 64, fused GP
-            mean 64 / 128), kernel-only, for context -- not part of the contract
+  gp_mean_128   the metric's second term (BASELINE configs[3]) at every N: 200 000 x 128x128 fp32 fused GP means
+            sharded over the ranks (strong scaling) + the final all_gather of the scalars, with its own
+            roofline ((n^2+3n+1) sizeof(T) per evaluation), e2e through invgpu_gp_host_f32 and cpu_baseline
+            (calcluateMeanCPU, src/gauss_cpu.c:23)
+  mixed     BASELINE configs[4] at every N: 500 000 mixed-dimension matrices per GPU (4 M on 8 GPUs)
+  extra     (N = 1 only) the other shapes, kernel-only, for context -- not part of the contract
 """
 from __future__ import annotations
 
@@ -33,7 +39,17 @@ import sys
 import threading
 import time
 
-import numpy as np
+# The CPU baseline runs the reference's OpenMP loops with every host core.  libgomp latches OMP_NUM_THREADS when
+# it is first loaded (torch loads it) and torchrun exports OMP_NUM_THREADS=1 to its workers, so the variable is set
+# here, before numpy / torch are imported; OpenBLAS stays single-threaded inside the OMP regions.
+try:
+    CPU_THREADS = len(os.sched_getaffinity(0))
+except AttributeError:
+    CPU_THREADS = os.cpu_count() or 1
+os.environ["OMP_NUM_THREADS"] = str(CPU_THREADS)
+os.environ["OPENBLAS_NUM_THREADS"] = "1"
+
+import numpy as np  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -43,6 +59,13 @@ BATCH = 1 << 20
 METRIC = "batched SPD inversions/sec (32x32 fp32)"
 UNIT = "inversions/s"
 WORKLOAD = "synthetic batched SPD Cholesky inverse, 2^20 x 32x32 fp32 per GPU (BASELINE configs[2])"
+# the metric's second term (BASELINE configs[3]): fused GP mean, 200 000 x 128x128 fp32 in total, sharded over the GPUs
+GP_N = 128
+GP_BATCH = 200_000
+GP_METRIC = "fused GP-mean evaluations/sec (128x128 fp32)"
+GP_UNIT = "evaluations/s"
+# BASELINE configs[4]: mixed dimensions, 4 M matrices on 8 GPUs = 500 000 per GPU (weak scaling)
+MIXED_PER_GPU = 500_000
 # dram__bytes_read.sum + dram__bytes_write.sum of the headline kernel from the committed `ncu --set full` capture
 # (2^18 matrices per launch there: 1.075257 GB read + 1.026820 GB written), scaled to the 2^20 of one bench launch
 NCU_DRAM_BYTES_PER_LAUNCH = int((1.075257e9 + 1.026820e9) * 4)
@@ -116,26 +139,57 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def _host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def _cpu_reference(sample: int, reps: int):
-    """The reference's CPU SPD inverse on `sample` 32x32 matrices, all host cores."""
+    """The reference's CPU SPD inverse on `sample` 32x32 matrices, all host cores.  The routine works in place, so
+    the input is refreshed before every repetition OUTSIDE the timed region (as src/inverse_bench.c:88-97 does)."""
     import oracle as orc
-    cores = os.cpu_count() or 1
-    os.environ["OMP_NUM_THREADS"] = str(cores)
-    os.environ["OPENBLAS_NUM_THREADS"] = "1"
+    cores = CPU_THREADS
     rng = np.random.default_rng(1234)
     r = rng.random((sample, N, N), dtype=np.float32)
     a = (r + r.transpose(0, 2, 1) + N * np.eye(N, dtype=np.float32)).reshape(-1)
+    work = np.empty_like(a)
     if orc.ref_available():
-        kind, fn = "reference", lambda: orc.ref_chol_inverse_upper(a, N)
+        kind, fn = "reference", lambda: orc.ref_chol_inverse_inplace(work, N)
         what = "oracle/_ref inverse_chol_blas_omp (reference src/inverse.c:100, OpenBLAS 0.3.15)"
     else:
-        kind, fn = "port", lambda: orc.chol_inverse(a, N)
+        out, info = np.empty_like(a), np.zeros(sample, dtype=np.int32)
+        kind, fn = "port", lambda: orc.chol_inverse(work, N)
         what = "oracle port orc_chol_inverse_batch_f32 (OpenMP)"
-    fn()
     times = []
-    for _ in range(reps):
+    for _ in range(reps + 1):
+        np.copyto(work, a)
         t0 = time.perf_counter(); fn(); times.append(time.perf_counter() - t0)
-    return kind, cores, what, times
+    return kind, cores, what, times[1:]
+
+
+def _cpu_reference_gp(n: int, sample: int, reps: int):
+    """The reference's CPU GP mean (calcluateMeanCPU, src/gauss_cpu.c:23) on `sample` evaluations, all host cores;
+    it destroys Bs / Cs, which are refreshed outside the timed region."""
+    import oracle as orc
+    rng = np.random.default_rng(4321)
+    r = rng.random((sample, n, n), dtype=np.float32)
+    b = (r + r.transpose(0, 2, 1) + n * np.eye(n, dtype=np.float32)).reshape(-1)
+    a, c, d = (rng.random(sample * n, dtype=np.float32) for _ in range(3))
+    out = np.zeros(sample, dtype=np.float32)
+    wb, wc = np.empty_like(b), np.empty_like(c)
+    if orc.ref_available():
+        kind, fn = "reference", lambda: orc.ref_gp_mean_inplace(n, a, wb, wc, d, out)
+        what = "oracle/_ref calcluateMeanCPU (reference src/gauss_cpu.c:23, OpenBLAS 0.3.15)"
+    else:
+        kind, fn = "port", lambda: orc.gp_mean(n, a, wb, wc, d)
+        what = "oracle port orc_gp_batch_f32 (OpenMP)"
+    times = []
+    for _ in range(reps + 1):
+        np.copyto(wb, b); np.copyto(wc, c)
+        t0 = time.perf_counter(); fn(); times.append(time.perf_counter() - t0)
+    return kind, CPU_THREADS, what, times[1:]
 
 
 def run_reference(args):
@@ -147,14 +201,18 @@ def run_reference(args):
     times = times[args.warmup:]
     total = sum(times)
     value = sample * len(times) / total
+    gk, _, gwhat, gtimes = _cpu_reference_gp(GP_N, 8192, 3)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "n": N, "sample_per_step": sample},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
-                         "sample": f"{sample} matrices per step, {what}, OMP_NUM_THREADS={cores}"},
+                         "sample": f"{sample} matrices per step, {what}, OMP_NUM_THREADS={cores}; the in-place routine's "
+                                   "input is refreshed outside the timed region"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gp_mean_128": {"metric": GP_METRIC, "value": 8192 / min(gtimes), "unit": GP_UNIT, "kind": gk, "cores": cores,
+                        "sample": f"8192 evaluations, best of 3, {gwhat}"},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
@@ -235,17 +293,22 @@ def _extras(torch, api, steps, warmup, hbm_peak):
     gp_case("gp_mean_64_f32", 64, 100 * 1600)
     gp_case("gp_mean_128_f32_25k", 128, 25000)
 
-    # BASELINE config 5, one GPU's share (4 M matrices over 8 GPUs = 500 k): mixed dimensions,
-    # P(n<=32)=.75 U{4..32}, P(<=128)=.20 U{33..128}, P(<=256)=.05 U{129..256}, seed 777
-    rng = np.random.default_rng(777)
-    cnt = 500_000
+    return out
+
+
+def _mixed_workload(torch, rank):
+    """BASELINE config 5, one GPU's share (4 M matrices over 8 GPUs = 500 k per GPU): mixed dimensions,
+    P(n<=32)=.75 U{4..32}, P(<=128)=.20 U{33..128}, P(<=256)=.05 U{129..256}, seed 777 (+ rank)."""
+    f32 = torch.float32
+    rng = np.random.default_rng(777 + rank)
+    cnt = MIXED_PER_GPU
     u = rng.random(cnt)
     ns = np.where(u < 0.75, rng.integers(4, 33, cnt), np.where(u < 0.95, rng.integers(33, 129, cnt), rng.integers(129, 257, cnt))).astype(np.int32)
     offs = np.concatenate([[0], np.cumsum(ns.astype(np.int64) ** 2)])
     total = int(offs[-1])
     buf = torch.empty(total, device="cuda", dtype=f32)
     # SPD per matrix: fill with U(0,1)/n (|off-diagonal row sum| < 1) then put 2 on the diagonals -> diagonally dominant
-    buf.uniform_(0.0, 1.0, generator=torch.Generator(device="cuda").manual_seed(777))
+    buf.uniform_(0.0, 1.0, generator=torch.Generator(device="cuda").manual_seed(777 + rank))
     scale = torch.from_numpy(np.repeat(1.0 / ns, ns.astype(np.int64) ** 2).astype(np.float32)).cuda()
     buf.mul_(scale)
     del scale
@@ -258,20 +321,37 @@ def _extras(torch, api, steps, warmup, hbm_peak):
     pin = (buf.data_ptr() + offs[:-1] * 4).astype(np.uint64)
     pout = (outb.data_ptr() + offs[:-1] * 4).astype(np.uint64)
     info = torch.zeros(cnt, dtype=torch.int32, device="cuda")
-    t = _time_kernel(torch, lambda: api.mixed_spd_inverse_device(pin, pout, ns, np.float32, info.data_ptr(), st), 3, 2)
-    ms = float(np.median(t))
-    gbs = 2 * 4 * total / (ms * 1e-3) / 1e9
-    out["mixed_500k_f32"] = {"matrices_per_s": cnt / (ms * 1e-3), "ms": ms, "algorithmic_GBps": gbs, "hbm_frac": gbs / hbm_peak,
-                             "flagged": int((info != 0).sum()), "tier": "persistent grids over nine padded sweep tiers (16/24/32/48/64/96/128/192/256), counting-sort work lists",
-                             "note": "timing includes the host-side planning (~1 ms, multi-threaded counting sort) and work-list upload"}
-    return out
+    return ns, total, buf, outb, pin, pout, info
+
+
+class PinnedF32:
+    """float32 host buffer from the engine's pinned allocator (invgpu_host_alloc), viewed as numpy / torch."""
+
+    def __init__(self, lib, count):
+        import ctypes as C
+        self.lib, self.count = lib, count
+        self.ptr = lib.invgpu_host_alloc(count * 4)
+        assert self.ptr, "invgpu_host_alloc failed"
+        self.np = np.ctypeslib.as_array(C.cast(self.ptr, C.POINTER(C.c_float)), shape=(count,))
+
+    def torch(self, torch):
+        return torch.from_numpy(self.np)
+
+    def free(self):
+        if self.ptr:
+            self.np = None
+            self.lib.invgpu_host_free(self.ptr)
+            self.ptr = None
 
 
 def run_ours(args):
+    import ctypes as C
+
     import torch
     import torch.distributed as dist
 
     from cuda_matrix_inversion_b200 import api, lib
+    from cuda_matrix_inversion_b200.sharding import gather_shards, shard_bounds
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -283,6 +363,45 @@ def run_ours(args):
     hbm_peak, peak_src = _peaks()
     stream = torch.cuda.current_stream().cuda_stream
 
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return float(x)
+        t = torch.tensor([x], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed_device(step, steps, warmup):
+        """W warm-up steps, then K steps bracketed by barrier + synchronize; CUDA events on the launch stream."""
+        for _ in range(warmup):
+            step()
+        barrier()
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        barrier()
+        evs[0].record()
+        for i in range(steps):
+            step()
+            evs[i + 1].record()
+        barrier()
+        per = [evs[i].elapsed_time(evs[i + 1]) for i in range(steps)]
+        return max_over_ranks(evs[0].elapsed_time(evs[-1])), per
+
+    def timed_host(step, steps, warmup):
+        """Host-flavour (synchronous) calls: wall clock around K calls after a barrier, max over ranks."""
+        for _ in range(warmup):
+            step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step()
+        torch.cuda.synchronize()
+        return max_over_ranks(time.perf_counter() - t0)
+
+    # ================================================================ headline: 2^20 x 32x32 fp32 SPD inverse per GPU
     a = _spd_device(torch, N, BATCH, torch.float32, 1234 + rank)
     inv = torch.empty_like(a)
     info = torch.zeros(BATCH, dtype=torch.int32, device="cuda")
@@ -290,28 +409,16 @@ def run_ours(args):
     def step():
         api.spd_inverse_device(a.data_ptr(), inv.data_ptr(), N, BATCH, np.float32, info.data_ptr(), stream)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()                      # before the warm-up: nvidia-smi needs ~0.2 s before its first sample
-    for _ in range(max(args.warmup, 3)):
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
         step()
     barrier()
     sampler.mark()
     launches0 = api.launch_count()
-    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    barrier()
-    evs[0].record()
-    for i in range(args.steps):
-        step()
-        evs[i + 1].record()
-    barrier()
-    per_step = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
-    total_ms = evs[0].elapsed_time(evs[-1])
+    total_ms_max, per_step = timed_device(step, args.steps, 0)
     launches = api.launch_count() - launches0
     if rank == 0:
         # the timed region is tens of milliseconds, nvidia-smi samples every 100 ms: keep the same kernel running
@@ -322,55 +429,144 @@ def run_ours(args):
             torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
     assert int(info.abs().max()) == 0
-    t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms_max = float(t.item())
     value = world * BATCH * args.steps / (total_ms_max * 1e-3)
     kernel_ms = float(np.mean(per_step))
     algo_bytes = 2 * N * N * 4 * BATCH
     achieved = algo_bytes / (kernel_ms * 1e-3) / 1e9
 
     # ---- end to end through the reference-facing host call: pinned HOST in -> HOST out
-    h_in = torch.empty(BATCH * N * N, dtype=torch.float32).pin_memory()
-    h_out = torch.empty(BATCH * N * N, dtype=torch.float32).pin_memory()
-    h_in.copy_(a.reshape(-1))
+    h_in, h_out = PinnedF32(lib, BATCH * N * N), PinnedF32(lib, BATCH * N * N)
+    h_in.torch(torch).copy_(a.reshape(-1))
     h_info = np.zeros(BATCH, dtype=np.int32)
-    import ctypes as C
-    pin, pout, pinfo = h_in.data_ptr(), h_out.data_ptr(), h_info.ctypes.data_as(C.c_void_p)
+    pinfo = h_info.ctypes.data_as(C.c_void_p)
 
     def e2e_step():
-        rc = lib.invgpu_spd_inverse_host_f32(pin, pout, N, BATCH, pinfo)
+        rc = lib.invgpu_spd_inverse_host_f32(h_in.ptr, h_out.ptr, N, BATCH, pinfo)
         assert rc == 0, rc
 
     e2e_steps = max(2, min(args.steps, 5))
-    for _ in range(2):
-        e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * BATCH * e2e_steps / float(t.item())
-    assert torch.equal(h_out[: 1024 * N * N].cuda(), inv.reshape(-1)[: 1024 * N * N])
-    del h_in, h_out
+    e2e_s = timed_host(e2e_step, e2e_steps, 2)
+    e2e_value = world * BATCH * e2e_steps / e2e_s
+    assert torch.equal(h_out.torch(torch)[: 1024 * N * N].cuda(), inv.reshape(-1)[: 1024 * N * N])
 
-    # final gather: one checksum scalar per rank (the only inter-GPU exchange of the workload)
+    # ---- the ceiling of that call on this box: the same pipeline (chunks, streams, ring) with the kernel replaced by a
+    # device copy (invgpu_xfer_roundtrip_host) -- copy-only, same bytes per step, same ranks concurrently
+    def ceil_step():
+        rc = lib.invgpu_xfer_roundtrip_host(h_in.ptr, h_out.ptr, N * N * 4, BATCH)
+        assert rc == 0, rc
+
+    ceil_s = timed_host(ceil_step, e2e_steps, 1)
+    ceil_value = world * BATCH * e2e_steps / ceil_s
+    h_in.free(); h_out.free()
+
+    # final gather: one checksum scalar per rank (the only inter-GPU exchange of this workload)
     chk = inv.double().sum().reshape(1)
     if world > 1:
-        from cuda_matrix_inversion_b200.sharding import gather_shards
         chk = gather_shards(chk, world).sum().reshape(1)
+    del a, inv, info
+    torch.cuda.empty_cache()
+    lib.invgpu_release_workspace()
+
+    # ================================================================ GP mean: 200 000 x 128x128 fp32 in total, sharded
+    lo, hi = shard_bounds(GP_BATCH, world, rank)
+    gb = hi - lo
+    n = GP_N
+    gen = torch.Generator(device="cuda").manual_seed(4321 + rank)
+    gB = _spd_device(torch, n, gb, torch.float32, 4322 + rank)
+    gA, gC, gD = (torch.rand((gb, n), generator=gen, device="cuda") for _ in range(3))
+    per = -(-GP_BATCH // world)
+    g_means = torch.zeros(per, device="cuda")                 # the fused kernel writes straight into the gather's send buffer
+    g_info = torch.zeros(gb, dtype=torch.int32, device="cuda")
+
+    def gp_step():
+        api.gp_device(n, gA.data_ptr(), gB.data_ptr(), gC.data_ptr(), gD.data_ptr(), 0, g_means.data_ptr(), 0, gb, np.float32,
+                      g_info.data_ptr(), stream)
+
+    gp_steps = max(3, min(args.steps, 10))
+    gl0 = api.launch_count()
+    gp_ms_max, gp_per = timed_device(gp_step, gp_steps, 3)
+    gp_launches = api.launch_count() - gl0
+    assert int(g_info.abs().max()) == 0
+    gp_value = GP_BATCH * gp_steps / (gp_ms_max * 1e-3)       # strong scaling: the 200 000 evaluations are the whole job
+    gp_kernel_ms = float(np.mean(gp_per))
+    gp_algo = ((n * n + 3 * n) * 4 + 4) * gb
+    gp_ach = gp_algo / (gp_kernel_ms * 1e-3) / 1e9
+    # the final gather of the scalars (the path's only collective): all_gather of ceil(B/G) floats per rank
+    gather_ms = 0.0
+    if world > 1:
+        outs = [torch.empty_like(g_means) for _ in range(world)]
+        for _ in range(2):
+            dist.all_gather(outs, g_means)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        dist.all_gather(outs, g_means)
+        e1.record()
+        torch.cuda.synchronize()
+        gather_ms = max_over_ranks(e0.elapsed_time(e1))
+        all_means = torch.cat(outs)[:GP_BATCH]
+    else:
+        all_means = g_means[:GP_BATCH]
+    gp_checksum = float(all_means.double().sum().item())
+    # parity spot check of this run's numbers against fp64 torch on a slice
+    kk = min(gb, 64)
+    m64 = gB[:kk].double() + torch.diag_embed(gC[:kk].double())
+    ref64 = (gA[:kk].double().unsqueeze(1) @ torch.linalg.solve(m64, gD[:kk].double().unsqueeze(2))).reshape(-1)
+    assert float((g_means[:kk].double() - ref64).abs().max()) <= 1e-4
+    # end to end: pinned host A, B, C, D in -> host means out through invgpu_gp_host_f32 (== calcluateMeanGPU)
+    hB, hA, hC, hD = PinnedF32(lib, gb * n * n), PinnedF32(lib, gb * n), PinnedF32(lib, gb * n), PinnedF32(lib, gb * n)
+    hB.torch(torch).copy_(gB.reshape(-1)); hA.torch(torch).copy_(gA.reshape(-1))
+    hC.torch(torch).copy_(gC.reshape(-1)); hD.torch(torch).copy_(gD.reshape(-1))
+    h_means = np.zeros(gb, dtype=np.float32)
+    h_ginfo = np.zeros(gb, dtype=np.int32)
+
+    def gp_e2e_step():
+        rc = lib.invgpu_gp_host_f32(n, hA.ptr, hB.ptr, hC.ptr, hD.ptr, None, h_means.ctypes.data, None, gb, h_ginfo.ctypes.data)
+        assert rc == 0, rc
+
+    gp_e2e_steps = 3
+    gp_e2e_s = timed_host(gp_e2e_step, gp_e2e_steps, 1)
+    gp_e2e_value = GP_BATCH * gp_e2e_steps / gp_e2e_s
+    assert np.array_equal(h_means[:1024], g_means[:1024].cpu().numpy())
+
+    # copy-only ceiling of that call: the same bytes host -> device, nothing else
+    def gp_ceil_step():
+        gB.reshape(-1).copy_(hB.torch(torch), non_blocking=True)
+        gA.reshape(-1).copy_(hA.torch(torch), non_blocking=True)
+        gC.reshape(-1).copy_(hC.torch(torch), non_blocking=True)
+        gD.reshape(-1).copy_(hD.torch(torch), non_blocking=True)
+        torch.cuda.synchronize()
+
+    gp_ceil_s = timed_host(gp_ceil_step, gp_e2e_steps, 1)
+    gp_ceil_value = GP_BATCH * gp_e2e_steps / gp_ceil_s
+    for h in (hB, hA, hC, hD):
+        h.free()
+    del gA, gB, gC, gD, g_means, g_info
+    torch.cuda.empty_cache()
+    lib.invgpu_release_workspace()
+
+    # ================================================================ mixed dimensions: 500 000 matrices per GPU
+    ns, mtotal, mbuf, mout, mpin, mpout, minfo = _mixed_workload(torch, rank)
+    ml0 = api.launch_count()
+    mixed_ms_max, mixed_per = timed_device(lambda: api.mixed_spd_inverse_device(mpin, mpout, ns, np.float32, minfo.data_ptr(), stream), 3, 2)
+    mixed_launches = (api.launch_count() - ml0) // 5
+    mixed_flagged = int((minfo != 0).sum())
+    mixed_value = world * MIXED_PER_GPU * 3 / (mixed_ms_max * 1e-3)
+    mixed_ms = float(np.mean(mixed_per))
+    mixed_gbs = 2 * 4 * mtotal / (mixed_ms * 1e-3) / 1e9
+    del mbuf, mout, minfo
+    torch.cuda.empty_cache()
+    lib.invgpu_release_workspace()
 
     if rank == 0:
-        kind, cores, what, times = _cpu_reference(1 << 18, 4)
-        cpu_value = (1 << 18) / min(times[1:])
+        kind, cores, what, times = _cpu_reference(1 << 18, 3)
+        cpu_value = (1 << 18) / min(times)
+        gkind, _, gwhat, gtimes = _cpu_reference_gp(GP_N, 8192, 3)
+        gp_cpu_value = 8192 / min(gtimes)
+        h2d, d2h = BATCH * N * N * 4, BATCH * N * N * 4 + BATCH * 4
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
+            "warmup": warm, "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "n": N, "batch_per_gpu": BATCH, "algorithm": "Cholesky-route inverse (potrf+trtri+lauum merged into one symmetric sweep; TMA tile I/O, sweep_kernels.cuh)",
                        "l2_policy": "inputs+outputs 8.6 GB per step >> 126 MB L2", "sharding": f"dp{world}",
@@ -381,16 +577,42 @@ def run_ours(args):
                          "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": kernel_ms},
             "cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": cores, "kind": kind,
                              "sample": f"{1 << 18} matrices (1/4 of the GPU batch), best of 3, {what}, "
-                                       f"OMP_NUM_THREADS={cores}"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": BATCH * N * N * 4,
-                    "d2h_bytes_per_step": BATCH * N * N * 4 + BATCH * 4, "steps": e2e_steps,
-                    "api": "invgpu_spd_inverse_host_f32 (pinned host buffers)"},
+                                       f"OMP_NUM_THREADS={cores} (set before libgomp loads); input refreshed outside the timed region"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                    "api": "invgpu_spd_inverse_host_f32 (pinned host buffers from invgpu_host_alloc)",
+                    "per_gpu": e2e_value / world, "host_GBps_aggregate": world * (h2d + d2h) * e2e_steps / e2e_s / 1e9,
+                    "ceiling": ceil_value, "frac_of_ceiling": e2e_value / ceil_value,
+                    "ceiling_what": "invgpu_xfer_roundtrip_host: the same host pipeline with the kernel replaced by a device copy, "
+                                    "same bytes, all ranks concurrently"},
+            "e2e_ceiling": ceil_value,
+            "gp_mean_128": {
+                "metric": GP_METRIC, "value": gp_value, "unit": GP_UNIT, "scaling": "strong", "batch_total": GP_BATCH,
+                "batch_per_gpu": gb, "steps": gp_steps, "ms_per_step": gp_ms_max / gp_steps, "dtype": "f32",
+                "config": {"workload": "fused GP mean A^T (B + diag C)^-1 D, 200 000 x 128x128 fp32 (BASELINE configs[3]), "
+                                       f"contiguous shards over {world} GPU(s), final all_gather of the scalars",
+                           "kernel_tier": api.tier_name("gp", n)},
+                "roofline": {"bound": "hbm", "achieved": gp_ach, "peak": hbm_peak, "unit": "GB/s", "frac": gp_ach / hbm_peak,
+                             "algorithmic_bytes_per_launch": gp_algo, "kernel_ms": gp_kernel_ms, "traffic": None,
+                             "fp32_flops_per_eval": n ** 3 / 3 + 2 * n * n + 3 * n},
+                "gather_ms": gather_ms, "checksum": gp_checksum, "gpu_launches": gp_launches,
+                "e2e": {"value": gp_e2e_value, "unit": GP_UNIT, "h2d_bytes_per_step": gb * (n * n + 3 * n) * 4,
+                        "d2h_bytes_per_step": gb * 8, "steps": gp_e2e_steps, "api": "invgpu_gp_host_f32 (== calcluateMeanGPU), pinned host buffers",
+                        "ceiling": gp_ceil_value, "frac_of_ceiling": gp_e2e_value / gp_ceil_value,
+                        "ceiling_what": "cudaMemcpyAsync of the same input bytes host -> device, all ranks concurrently"},
+                "cpu_baseline": {"value": gp_cpu_value, "unit": GP_UNIT, "cores": cores, "kind": gkind,
+                                 "sample": f"8192 evaluations, best of 3, {gwhat}, OMP_NUM_THREADS={cores}"},
+            },
+            "mixed": {
+                "metric": "mixed-dimension SPD inversions/sec (n in 4..256, BASELINE configs[4])", "value": mixed_value,
+                "unit": "matrices/s", "scaling": "weak", "matrices_per_gpu": MIXED_PER_GPU, "matrices_total": world * MIXED_PER_GPU,
+                "ms_per_step": mixed_ms_max / 3, "algorithmic_GBps_per_gpu": mixed_gbs, "hbm_frac": mixed_gbs / hbm_peak,
+                "flagged": mixed_flagged, "kernels_per_step": mixed_launches,
+                "note": "timing includes the host-side planning (multi-threaded counting sort) and the work-list upload",
+            },
             "gpu_launches": launches, "clocks": clocks, "checksum": float(chk.item()),
         }
         if not args.no_extra and world == 1:
-            del a, inv
-            torch.cuda.empty_cache()
-            lib.invgpu_release_workspace()
             line["extra"] = _extras(torch, api, 5, 3, hbm_peak)
         print(json.dumps(line), flush=True)
     if world > 1:

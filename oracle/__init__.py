@@ -208,6 +208,20 @@ def ref_chol_inverse_upper(flat32: np.ndarray, n: int) -> np.ndarray:
     return buf
 
 
+def ref_chol_inverse_inplace(buf32: np.ndarray, n: int) -> None:
+    """inverse_chol_blas_omp on the caller's own float32 buffer, no copy: what bench.py times (the reference's own
+    bench refreshes its input OUTSIDE the timed region too, src/inverse_bench.c:88-97)."""
+    assert buf32.dtype == np.float32 and buf32.flags.c_contiguous
+    ref().inverse_chol_blas_omp(_p(buf32), C.c_int(n), C.c_int(buf32.size // (n * n)))
+
+
+def ref_gp_mean_inplace(n, a, b, c, d, out) -> None:
+    """calcluateMeanCPU on the caller's own float32 buffers (Bs and Cs are destroyed), no copies: bench.py's timed call."""
+    for v in (a, b, c, d, out):
+        assert v.dtype == np.float32 and v.flags.c_contiguous
+    ref().calcluateMeanCPU(C.c_int(n), _p(a), _p(b), _p(c), _p(d), _p(out), C.c_int(b.size // (n * n)))
+
+
 def ref_lu_inverse(flat32: np.ndarray, n: int) -> np.ndarray:
     """inverse_lu_blas_omp (reference src/inverse.c:71): in place."""
     buf = np.ascontiguousarray(flat32, dtype=np.float32).copy()

@@ -200,8 +200,11 @@ template <typename T>
 static int fast_gp(GpIO<T> io, int n, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds) {
     const uintptr_t all = (uintptr_t)io.a | (uintptr_t)io.b | (uintptr_t)io.c | (uintptr_t)io.d;
     if (all % 16 != 0 || ((size_t)n * sizeof(T)) % 16 != 0) return INVGPU_NO_FAST_PATH;
-    static int old = -1;                              // INVGPU_GP_KERNEL=tile keeps the three-phase tile kernels
-    if (old < 0) { const char *e = getenv("INVGPU_GP_KERNEL"); old = (e && !strcmp(e, "tile")) ? 1 : 0; }
+    static int old = -1, no_tc = -1;                  // INVGPU_GP_KERNEL=tile keeps the three-phase tile kernels, =sweep the CUDA-core sweep
+    if (old < 0) { const char *e = getenv("INVGPU_GP_KERNEL"); old = (e && !strcmp(e, "tile")) ? 1 : 0; no_tc = (e && !strcmp(e, "sweep")) ? 1 : 0; }
+    if constexpr (std::is_same<T, float>::value) {    // n = 128 fp32: blocked Cholesky with the tcgen05 trailing update (tc_kernels.cuh)
+        if (n == 128 && !old && !no_tc) return launch_tc_gp128(io, batch, dInfo, st, ds);
+    }
     static int variant = -1;                          // INVGPU_SWEEP_VARIANT=V: another instantiated configuration
     if (variant < 0) { const char *e = getenv("INVGPU_SWEEP_VARIANT"); variant = e ? atoi(e) : 0; }
 #define INVGPU_GP_THREAD_TRY(TT, N, WARPS, MINB)                                                    \
@@ -248,6 +251,7 @@ static int fast_padded(PadIO<T> io, int tier_n, i64 batch, int *dInfo, cudaStrea
 #define INVGPU_SWEEP_GP_NAME(V, TT, N, TR, TC, UNROLL, MINB, BLK) \
     if (op == 2 && V == 0 && n == N && dtype_bytes == (int)sizeof(TT)) return TR * TC <= 32 ? "sweep-warp" : "sweep-cta";
 static const char *fast_tier_name(int op, int n, int dtype_bytes) {
+    if (op == 2 && n == 128 && dtype_bytes == 4) return "tcgen05-blocked";
     INVGPU_SPD8_TMA_ALL(INVGPU_SPD8_NAME)
     INVGPU_THREAD_BULK_ALL(INVGPU_THREAD_BULK_NAME)
     INVGPU_SWEEP_ALL(INVGPU_SWEEP_NAME)

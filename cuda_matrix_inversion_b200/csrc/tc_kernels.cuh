@@ -1,0 +1,375 @@
+// tc_kernels.cuh -- n = 128 fp32 on the 5th-generation tensor cores: blocked factorisation with the
+// MATRIX ITSELF AS THE TMEM ACCUMULATOR (128 lanes x 128 columns of fp32 = one 128x128 matrix; lane = row).
+//
+// north_star: "Tensor cores are used only for the trailing-update GEMM of blocked n >= 64 factorizations, and
+// only where ncu shows it wins."  This is that kernel for the fused GP mean / variance (BASELINE configs[3];
+// replaces addDiagonal -> getrf/getriBatched -> gemv -> dot of reference src/gauss_bench.cu:38-265 like the CUDA-core
+// kernels of sweep_kernels.cuh do):
+//
+//   one CTA of 128 threads per evaluation, thread t = row t of B + diag C, warp w <-> TMEM lanes 32w..32w+31.
+//   Right-looking blocked Cholesky, panel width 32:
+//     panel p:  tcgen05.ld the 32 panel columns of every row (lane = row: 32 registers per thread)
+//               warp p factors the 32x32 diagonal block (lane = row, column k published through shared memory,
+//               rsqrt + one Newton step per pivot) and forward-substitutes both right-hand sides along the way
+//               warps > p solve their rows against it (row TRSM: 496 FMAs per thread, broadcast LDS operands)
+//               every row writes its 32 multipliers to shared memory as a K-major UMMA operand, split
+//               x = hi + lo with hi = the TF32-representable head (3xTF32: hi*hi + hi*lo + lo*hi ~ fp32 accuracy)
+//               one thread issues 12 tcgen05.mma.kind::tf32 (4 K-steps x 3 split products, M = 128,
+//               N = 128 - 32(p+1), A negated by the instruction descriptor):  T[:, 32(p+1):] -= L_p L_p^T,
+//               tcgen05.commit -> mbarrier; the next panel's tcgen05.ld waits on it
+//   so the n^3/3 flops of the factorisation shrink to the 34 % that are panel work on the CUDA cores; the
+//   right-hand sides ride along in registers (32 FMAs per thread, vector and panel) and the result is
+//   sum_k y_k(a) y_k(d) -- no inverse, no solve vectors and no intermediates reach HBM.
+//   Only the UPPER triangle of B is read (spotrf_("U") convention of the reference's CPU path, src/gauss_cpu.c:54):
+//   row i of the lower triangle = the first i+1 elements of column i of the column-major input.
+//   Pivots are taken in natural order, so `info` is spotrf's directly.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace invgpu {
+namespace tc {
+
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+// bounded wait: a protocol error traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    const uint32_t a = smem_addr(bar);
+    for (uint32_t spin = 0;; ++spin) {
+        uint32_t done;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(a), "r"(parity) : "memory");
+        if (done) return;
+        if (spin > (1u << 26)) __trap();
+    }
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t *slot, uint32_t cols) {      // one full warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(slot)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {    // the same warp
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// 32 consecutive columns of the calling thread's TMEM lane <-> 32 registers
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    #pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    #pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+                 "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+                 "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+                 :: "r"(taddr),
+                    "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+                    "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+                    "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+                    "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])),
+                    "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])), "r"(__float_as_uint(v[19])),
+                    "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])), "r"(__float_as_uint(v[23])),
+                    "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])), "r"(__float_as_uint(v[27])),
+                    "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// Shared-memory operand descriptor, K-major, no swizzle ("interleave"): core matrices of 8 rows x 16 bytes are
+// 128 contiguous bytes; the next 8-row group lies SBO bytes further, the next 16-byte K chunk LBO bytes further.
+// Bit layout as in cute::UMMA::SmemDescriptor (cute/arch/mma_sm100_desc.hpp): start >> 4 in [0,14), LBO >> 4 in
+// [16,30), SBO >> 4 in [32,46), version 1 in [46,48), layout type 0 in [61,64).
+__device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32) | (1ull << 46);
+}
+// Instruction descriptor of kind::tf32 (cute::UMMA::InstrDescriptor): D = F32 (1 << 4), A = B = TF32 (2 << 7, 2 << 10),
+// negate A (1 << 13), both K-major, N >> 3 in [17,23), M >> 4 in [24,29).
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int m, int n, bool negate_a) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((negate_a ? 1u : 0u) << 13) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, issued by ONE thread
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+                 :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+
+constexpr int GP_N = 128;          // matrix order == TMEM lanes == threads per CTA
+constexpr int GP_CHUNK_STRIDE = GP_N * 16;                       // LBO: bytes between 16-byte K chunks of an operand (2048)
+
+template <int PW>
+struct __align__(16) GpShared {
+    float lcol[PW * PW];           // lcol[k * PW + i] = L11(k + 1 + i, k): column k of the current diagonal block, aligned
+    float rinv[PW];                // 1 / L11(k, k)
+    float ya[PW], yd[PW];          // forward-substituted right-hand sides of the current panel
+    float red[2 * 4];
+    uint64_t mma_done;
+    uint32_t tmem_base;
+    int info;
+};
+template <int PW> struct GpGeo {
+    static constexpr int PANEL_BYTES = GP_N * PW * 4;            // one operand copy (hi or lo)
+    static constexpr size_t SMEM_BYTES = 2 * PANEL_BYTES + sizeof(GpShared<PW>);
+};
+
+// x[j] -= l * L11(j, K) for the columns j > K of the panel; col[i] = L11(K + 1 + i, K) (broadcast 128-bit reads).
+// Triangular and fully unrolled: every register index is static and only the FMAs that matter are issued (a rolled
+// full-width form with a rotating register window doubled both the FMAs and the shared-memory wavefronts, which are
+// what bounds this kernel: one broadcast word per FMA).
+template <int PW, int K>
+struct Tail {
+    static constexpr int NQ = (PW - K - 1 + 3) / 4;
+    float4 v[NQ > 0 ? NQ : 1];
+    __device__ __forceinline__ void load(const float *col) {
+        #pragma unroll
+        for (int q = 0; q < NQ; ++q) v[q] = reinterpret_cast<const float4 *>(col)[q];
+    }
+    __device__ __forceinline__ void apply(float (&x)[PW], float l) const {
+        #pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            if (K + 1 + 4 * q + 0 < PW) x[K + 1 + 4 * q + 0] = fmaf(-l, v[q].x, x[K + 1 + 4 * q + 0]);
+            if (K + 1 + 4 * q + 1 < PW) x[K + 1 + 4 * q + 1] = fmaf(-l, v[q].y, x[K + 1 + 4 * q + 1]);
+            if (K + 1 + 4 * q + 2 < PW) x[K + 1 + 4 * q + 2] = fmaf(-l, v[q].z, x[K + 1 + 4 * q + 2]);
+            if (K + 1 + 4 * q + 3 < PW) x[K + 1 + 4 * q + 3] = fmaf(-l, v[q].w, x[K + 1 + 4 * q + 3]);
+        }
+    }
+};
+template <int PW, int K>
+__device__ __forceinline__ void rank1_tail(float (&x)[PW], float l, const float *col) {
+    Tail<PW, K> tl;
+    tl.load(col);
+    tl.apply(x, l);
+}
+
+// reciprocal square root of a pivot (rsqrt.approx + one Newton step: full fp32 accuracy); a non-positive / NaN pivot is
+// recorded (spotrf's info = the first one) and replaced by 1 so that the rest of the panel stays finite
+__device__ __forceinline__ float pivot_rsqrt_newton(float d, int k1, int &bad_at) {
+    const bool bad = !(d > 0.f);                                  // uniform in the warp
+    bad_at = (bad && bad_at == 0) ? k1 : bad_at;
+    d = bad ? 1.f : d;
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
+    return r * fmaf(-0.5f * d * r, r, 1.5f);
+}
+
+// The warp that owns the diagonal block of a panel (lanes lane0 .. lane0 + PW - 1 = the block's rows; for PW = 16 the
+// other half-warp holds rows below the block, which simply follow as TRSM rows, or finished rows above it, whose
+// registers are don't-cares).  Pivot k:  shfl(dself, pivot lane) -> rsqrt -> l = x_k * r -> dself -= l^2: every lane
+// keeps its OWN diagonal element up to date locally, so the pivot chain never waits for the shared-memory exchange of
+// column k (store l, __syncwarp, broadcast loads, rank-1 tail), which runs beside it.  x[k] becomes the multiplier.
+// Measured alternatives (profiles/r2_tc_gp128_summary.md): starting pivot k+1's shuffle + rsqrt before step k's column
+// loads (-5 %), fetching L(k+1, k) by a fourth shuffle (-13 %: the SM retires one warp shuffle per clock), dropping the
+// Newton step, staggering the CTAs of an SM in time (0 %).
+template <int PW, int K>
+struct DiagStep {
+    static __device__ __forceinline__ void run(float (&x)[PW], float &dself, int &bad_at, float &ua, float &ud, float &ya, float &yd,
+                                               GpShared<PW> *sh, int lane, int lane0) {
+        const int pl = lane0 + K;                                 // pivot lane
+        const float r = pivot_rsqrt_newton(__shfl_sync(0xffffffffu, dself, pl), K + 1, bad_at);
+        const float l = x[K] * r;
+        x[K] = l;
+        dself = fmaf(-l, l, dself);
+        const float ta = __shfl_sync(0xffffffffu, ua * r, pl);
+        const float td = __shfl_sync(0xffffffffu, ud * r, pl);
+        if (lane == pl) { ya = ta; yd = td; }
+        ua = fmaf(-l, ta, ua);
+        ud = fmaf(-l, td, ud);
+        if (lane == 0) { sh->rinv[K] = r; sh->ya[K] = ta; sh->yd[K] = td; }
+        const int jb = lane - lane0;                              // row inside the block
+        if (jb > K && jb < PW) sh->lcol[K * PW + jb - K - 1] = l; // aligned column: entry i = L11(K + 1 + i, K)
+        __syncwarp();
+        rank1_tail<PW, K>(x, l, sh->lcol + K * PW);
+        DiagStep<PW, K + 1>::run(x, dself, bad_at, ua, ud, ya, yd, sh, lane, lane0);
+    }
+};
+template <int PW> struct DiagStep<PW, PW> {
+    static __device__ __forceinline__ void run(float (&)[PW], float &, int &, float &, float &, float &, float &, GpShared<PW> *, int, int) {}
+};
+
+// a row below the diagonal block (another warp): l_ik = x_k / L_kk, the row's own rank-1 tail and right-hand sides
+template <int PW, int K>
+struct TrsmStep {
+    static __device__ __forceinline__ void run(float (&x)[PW], float &ua, float &ud, const GpShared<PW> *sh) {
+        const float l = x[K] * sh->rinv[K];
+        x[K] = l;
+        ua = fmaf(-l, sh->ya[K], ua);
+        ud = fmaf(-l, sh->yd[K], ud);
+        rank1_tail<PW, K>(x, l, sh->lcol + K * PW);
+        TrsmStep<PW, K + 1>::run(x, ua, ud, sh);
+    }
+};
+template <int PW> struct TrsmStep<PW, PW> {
+    static __device__ __forceinline__ void run(float (&)[PW], float &, float &, const GpShared<PW> *) {}
+};
+
+template <int PW> __device__ __forceinline__ void tmem_ld_panel(uint32_t taddr, float (&x)[PW]);
+template <> __device__ __forceinline__ void tmem_ld_panel<32>(uint32_t taddr, float (&x)[32]) { tmem_ld32(taddr, x); }
+template <> __device__ __forceinline__ void tmem_ld_panel<16>(uint32_t taddr, float (&x)[16]) { tmem_ld16(taddr, x); }
+
+// Fused GP mean / variance, n = 128 fp32, panel width PW (16 or 32).  grid = persistent, block = 128.
+template <int PW, int MINB>
+__global__ void __launch_bounds__(128, MINB)
+tc_gp128_kernel(GpIO<float> io, i64 batch, int *__restrict__ info) {
+    using Geo = GpGeo<PW>;
+    constexpr int NP = GP_N / PW;                                 // panels
+    // no pointer arithmetic through integers here: the compiler must keep seeing the shared address space (a generic
+    // LD.E / ST.E costs ~30 clocks more than LDS / STS, and these accesses sit beside the pivot chain)
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char *l_hi = smem_raw, *l_lo = smem_raw + Geo::PANEL_BYTES;
+    GpShared<PW> *sh = reinterpret_cast<GpShared<PW> *>(smem_raw + 2 * Geo::PANEL_BYTES);
+    const int t = threadIdx.x, w = t >> 5, lane = t & 31;
+
+    if (w == 0) tmem_alloc(&sh->tmem_base, 128);
+    if (t == 0) { mbar_init(&sh->mma_done, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = sh->tmem_base;
+    const uint32_t my_lane = tmem + ((uint32_t)(32 * w) << 16);           // this warp's 32 TMEM lanes
+    uint32_t phase = 0;
+    // where this row's multipliers go inside an operand copy (K-major core matrices, see umma_desc_kmajor)
+    const uint32_t row_off = (uint32_t)(t >> 3) * 128u + (uint32_t)(t & 7) * 16u;
+
+    for (i64 m = blockIdx.x; m < batch; m += gridDim.x) {
+        const float *__restrict__ brow = io.b + m * (GP_N * GP_N) + (i64)t * GP_N;   // column t == row t of the symmetric input
+        const float cdiag = io.c[m * GP_N + t];
+        float ua = io.a[m * GP_N + t];
+        float ud = io.d ? io.d[m * GP_N + t] : ua;
+        if (t == 0) sh->info = 0;
+        if (m + gridDim.x < batch) {                                          // next evaluation of this CTA: its row prefix -> L2
+            const float *nrow = brow + (i64)gridDim.x * (GP_N * GP_N);
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nrow), "r"((uint32_t)(128 * (w + 1))) : "memory");
+        }
+        // ---- load: columns 32c..32c+31 of this row for c <= w (lower triangle), + diag C, into this row's TMEM lane
+        {
+            float v32[32];
+            #pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                if (c <= w) {                                                 // warp-uniform
+                    #pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const float4 v = __ldg(reinterpret_cast<const float4 *>(brow + 32 * c) + q);
+                        v32[4 * q + 0] = v.x; v32[4 * q + 1] = v.y; v32[4 * q + 2] = v.z; v32[4 * q + 3] = v.w;
+                    }
+                    if (c == w) {
+                        #pragma unroll
+                        for (int j = 0; j < 32; ++j) if (j == lane) v32[j] += cdiag;
+                    }
+                    tmem_st32(my_lane + 32 * c, v32);
+                }
+            }
+            tmem_st_wait();
+        }
+        float ya = 0.f, yd = 0.f;
+
+        #pragma unroll 1
+        for (int p = 0; p < NP; ++p) {
+            const int wd = (p * PW) >> 5;                                     // the warp that owns the diagonal block
+            const int lane0 = (p * PW) & 31;                                  // its first lane
+            float x[PW];
+            if (w >= wd) {
+                if (p > 0) { mbar_wait(&sh->mma_done, phase); tc_fence_after(); }   // the update of panel p-1 has landed
+                tmem_ld_panel<PW>(my_lane + PW * p, x);
+            }
+            if (p > 0) phase ^= 1;                                            // every thread tracks the barrier's phase
+            if (w == wd) {
+                float dself = 0.f;                                            // this lane's own diagonal element
+                #pragma unroll
+                for (int j = 0; j < PW; ++j) dself = (lane - lane0 == j) ? x[j] : dself;
+                int bad_at = 0;
+                DiagStep<PW, 0>::run(x, dself, bad_at, ua, ud, ya, yd, sh, lane, lane0);
+                if (lane == 0 && bad_at != 0 && sh->info == 0) sh->info = p * PW + bad_at;
+            }
+            __syncthreads();
+            if (w > wd) TrsmStep<PW, 0>::run(x, ua, ud, sh);
+            if (w >= wd && p < NP - 1) {                                      // publish the row's multipliers as hi + lo
+                #pragma unroll
+                for (int c = 0; c < PW / 4; ++c) {
+                    float4 hi, lo;
+                    hi.x = __uint_as_float(__float_as_uint(x[4 * c + 0]) & 0xffffe000u); lo.x = x[4 * c + 0] - hi.x;
+                    hi.y = __uint_as_float(__float_as_uint(x[4 * c + 1]) & 0xffffe000u); lo.y = x[4 * c + 1] - hi.y;
+                    hi.z = __uint_as_float(__float_as_uint(x[4 * c + 2]) & 0xffffe000u); lo.z = x[4 * c + 2] - hi.z;
+                    hi.w = __uint_as_float(__float_as_uint(x[4 * c + 3]) & 0xffffe000u); lo.w = x[4 * c + 3] - hi.w;
+                    *reinterpret_cast<float4 *>(l_hi + c * GP_CHUNK_STRIDE + row_off) = hi;
+                    *reinterpret_cast<float4 *>(l_lo + c * GP_CHUNK_STRIDE + row_off) = lo;
+                }
+                fence_async_smem();                                           // generic-proxy writes -> visible to the tensor core
+            }
+            tc_fence_before();
+            __syncthreads();
+            if (p < NP - 1 && t == 0) {
+                tc_fence_after();
+                const int n_cols = GP_N - PW * (p + 1);
+                const uint32_t idesc = umma_idesc_tf32(128, n_cols, true);
+                const uint32_t d_addr = tmem + PW * (p + 1);
+                const uint32_t b_rows = (uint32_t)(PW * (p + 1) / 8) * 128u;   // B operand = rows PW(p+1).. of the same panel
+                #pragma unroll
+                for (int ks = 0; ks < PW / 8; ++ks) {
+                    const uint32_t koff = (uint32_t)ks * 2u * GP_CHUNK_STRIDE;
+                    const uint64_t a_hi = umma_desc_kmajor(smem_addr(l_hi) + koff, GP_CHUNK_STRIDE, 128);
+                    const uint64_t a_lo = umma_desc_kmajor(smem_addr(l_lo) + koff, GP_CHUNK_STRIDE, 128);
+                    const uint64_t b_hi = umma_desc_kmajor(smem_addr(l_hi) + koff + b_rows, GP_CHUNK_STRIDE, 128);
+                    const uint64_t b_lo = umma_desc_kmajor(smem_addr(l_lo) + koff + b_rows, GP_CHUNK_STRIDE, 128);
+                    umma_tf32(d_addr, a_lo, b_hi, idesc, 1u);                 // small terms first
+                    umma_tf32(d_addr, a_hi, b_lo, idesc, 1u);
+                    umma_tf32(d_addr, a_hi, b_hi, idesc, 1u);
+                }
+                umma_commit(&sh->mma_done);
+            }
+        }
+        // ---- epilogue: means = sum ya*yd, variances = E - sum ya^2 (every row finalised its y in its own panel)
+        float pm = ya * yd, pq = ya * ya;
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { pm += __shfl_xor_sync(0xffffffffu, pm, o); pq += __shfl_xor_sync(0xffffffffu, pq, o); }
+        if (lane == 0) { sh->red[w] = pm; sh->red[4 + w] = pq; }
+        __syncthreads();
+        if (t == 0) {
+            const int st = sh->info;
+            const float sm = (sh->red[0] + sh->red[1]) + (sh->red[2] + sh->red[3]);
+            const float sq = (sh->red[4] + sh->red[5]) + (sh->red[6] + sh->red[7]);
+            if (info) info[m] = st;
+            if (io.means) io.means[m] = st ? dev_nan<float>() : sm;
+            if (io.variances) io.variances[m] = st ? dev_nan<float>() : io.e[m] - sq;
+        }
+        __syncthreads();                                                     // red / info reuse; all tensor-core work of this matrix is done
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (w == 0) tmem_dealloc(tmem, 128);
+}
+
+}  // namespace tc
+}  // namespace invgpu

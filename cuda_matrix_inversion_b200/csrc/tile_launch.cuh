@@ -48,6 +48,9 @@ int launch_spd_thread_bulk(StridedIO<T> io, i64 batch, int *dInfo, cudaStream_t 
 template <typename T, int N, int WARPS, int MINB>
 int launch_gp_thread(GpIO<T> io, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds);
 
+// tensor-core tier (tc_kernels.cuh, defined in inst_tc_f32.cu): fused GP mean / variance, n = 128 fp32
+int launch_tc_gp128(GpIO<float> io, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds);
+
 }  // namespace invgpu
 
 #ifdef INVGPU_TILE_DEFINE

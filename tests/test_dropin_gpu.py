@@ -179,35 +179,39 @@ def test_xfer_roundtrip_probe_copies_exactly():
 
 
 def test_batched_cuda_malloc_pitched_pointer_arrays(api):
-    """The allocation pattern of every upstream `_device` caller (src/gauss_bench.cu:160-167): pointer arrays in
-    host memory from batchedCudaMalloc, 512-byte pitch, lda = n."""
+    """The allocation pattern of every upstream `_device` caller (src/gauss_bench.cu:160-167): pointer arrays in PINNED
+    host memory (cudaHostAlloc upstream, batched_invert.cu:120-121) filled by batchedCudaMalloc, 512-byte pitch, lda = n."""
     import torch
     from cuda_matrix_inversion_b200 import lib
     n, batch = 24, 50
     lib.batchedCudaMalloc.restype = C.c_int
     lib.batchedCudaMalloc.argtypes = [C.c_void_p, C.POINTER(C.c_size_t), C.c_size_t, C.c_int]
-    ins, outs = (C.c_void_p * batch)(), (C.c_void_p * batch)()
+    ins = torch.zeros(batch, dtype=torch.int64).pin_memory()
+    outs = torch.zeros(batch, dtype=torch.int64).pin_memory()
     pitch = C.c_size_t(0)
-    assert lib.batchedCudaMalloc(ins, C.byref(pitch), n * n * 4, batch) == 0
-    assert lib.batchedCudaMalloc(outs, C.byref(pitch), n * n * 4, batch) == 0
-    assert pitch.value >= n * n * 4 and pitch.value % 512 == 0 and ins[1] - ins[0] == pitch.value
+    assert lib.batchedCudaMalloc(ins.data_ptr(), C.byref(pitch), n * n * 4, batch) == 0
+    assert lib.batchedCudaMalloc(outs.data_ptr(), C.byref(pitch), n * n * 4, batch) == 0
+    p = int(pitch.value)
+    assert p >= n * n * 4 and p % 512 == 0 and int(ins[1] - ins[0]) == p
     a = spd_batch(n, batch, np.float32, seed=5)
-    cudart = torch.cuda.cudart()
-    flat = orc.to_colmajor(a).reshape(batch, n * n)
-    for k in range(batch):
-        assert int(cudart.cudaMemcpy(ins[k], flat[k].ctypes.data, n * n * 4, 1)) == 0     # cudaMemcpyHostToDevice
-    lib.inverse_cholesky_batched_device(None, n, ins, outs, batch)
+    # the second runtime instance shares the primary context: plain cudaMemcpy on the raw pitched pointers
+    rt = C.CDLL("/usr/local/cuda/lib64/libcudart.so")
+    rt.cudaMemcpy2D.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int]
+    rt.cudaFree.argtypes = [C.c_void_p]
+    flat = np.ascontiguousarray(orc.to_colmajor(a).reshape(batch, n * n))
+    assert rt.cudaMemcpy2D(int(ins[0]), p, flat.ctypes.data, n * n * 4, n * n * 4, batch, 1) == 0     # host -> device
     got = np.empty((batch, n * n), dtype=np.float32)
-    torch.cuda.synchronize()
-    for k in range(batch):
-        assert int(cudart.cudaMemcpy(got[k].ctypes.data, outs[k], n * n * 4, 2)) == 0
-    assert residual_inf(a, orc.from_colmajor(got.reshape(-1), n)) <= 1e-4
-    lib.inverse_gauss_batched_device(None, n, ins, outs, batch)
-    torch.cuda.synchronize()
-    for k in range(batch):
-        assert int(cudart.cudaMemcpy(got[k].ctypes.data, outs[k], n * n * 4, 2)) == 0
-    assert residual_inf(a, orc.from_colmajor(got.reshape(-1), n)) <= 1e-4
-    assert int(cudart.cudaFree(ins[0])) == 0 and int(cudart.cudaFree(outs[0])) == 0
+
+    def fetch():
+        torch.cuda.synchronize()
+        assert rt.cudaMemcpy2D(got.ctypes.data, n * n * 4, int(outs[0]), p, n * n * 4, batch, 2) == 0  # device -> host
+        return orc.from_colmajor(got.reshape(-1), n)
+
+    lib.inverse_cholesky_batched_device(None, n, ins.data_ptr(), outs.data_ptr(), batch)
+    assert residual_inf(a, fetch()) <= 1e-4
+    lib.inverse_gauss_batched_device(None, n, ins.data_ptr(), outs.data_ptr(), batch)
+    assert residual_inf(a, fetch()) <= 1e-4
+    assert rt.cudaFree(int(ins[0])) == 0 and rt.cudaFree(int(outs[0])) == 0
 
 
 # ------------------------------------------------------------------ n up to 256 in every family, both dtypes
@@ -390,10 +394,11 @@ def test_legacy_lu_device_leaves_factors_in_devAs(api):
     flat = orc.to_colmajor(a)
     d_a = torch.from_numpy(flat.copy()).cuda()
     d_inv = torch.zeros_like(d_a)
-    pin = (C.c_void_p * batch)(*[d_a.data_ptr() + k * n * n * 4 for k in range(batch)])
-    pout = (C.c_void_p * batch)(*[d_inv.data_ptr() + k * n * n * 4 for k in range(batch)])
+    # pointer arrays in pinned host memory, as upstream allocates them (cudaHostAlloc, src/gauss/batched_invert.cu:120-121)
+    pin = torch.tensor([d_a.data_ptr() + k * n * n * 4 for k in range(batch)], dtype=torch.int64).pin_memory()
+    pout = torch.tensor([d_inv.data_ptr() + k * n * n * 4 for k in range(batch)], dtype=torch.int64).pin_memory()
     torch.cuda.synchronize()
-    lib.inverse_lu_cuda_batched_device(None, n, pin, pout, batch)
+    lib.inverse_lu_cuda_batched_device(None, n, pin.data_ptr(), pout.data_ptr(), batch)
     torch.cuda.synchronize()
     lu_o, _, _ = orc.getrf(flat, n)
     assert normwise_err(orc.from_colmajor(d_a.cpu().numpy(), n), orc.from_colmajor(lu_o, n)) <= 1e-4

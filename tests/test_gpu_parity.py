@@ -339,7 +339,7 @@ def test_gp_flags(api):
 
 @pytest.mark.parametrize("n", [64, 128])
 def test_gp_flags_cta_tiers(api, n):
-    """fp32 n = 128 runs on the sweep GP kernel (permuted order): flags must still be LAPACK's."""
+    """fp32 n = 128 runs on the tcgen05 tier (natural pivot order), n = 64 on the tile kernel: flags must be LAPACK's."""
     g = gp_batch(n, 5, np.float32, seed=19)
     g["b"][1] = -g["b"][1]
     d = np.ones(n, dtype=np.float32)
@@ -354,6 +354,59 @@ def test_gp_flags_cta_tiers(api, n):
     good = info == 0
     assert np.abs(means[good] - om[good]).max() <= 1e-4
     assert np.isnan(means[~good]).all()
+
+
+def test_gp_128_tensor_core_tier(api, torch):
+    """fp32 n = 128 runs on the tcgen05 tier (tc_kernels.cuh: blocked Cholesky, 3xTF32 trailing update with the matrix as
+    the TMEM accumulator).  Against the oracle and fp64 truth on (i) the reference generator's matrices, (ii) SPD matrices
+    with cond ~1e3 (the 3xTF32 split must hold the 1e-4 bar there, a single TF32 pass does not), (iii) a batch that makes
+    every CTA of the persistent grid loop (2 400 evaluations > 4 x 148), (iv) only the UPPER triangle may be read."""
+    n = 128
+    assert api.tier_name("gp", n, np.float32) == "tcgen05-blocked"
+    rng = np.random.default_rng(5)
+    # (ii) cond ~ 1e3: B = Q diag(s) Q^T
+    q, _ = np.linalg.qr(rng.standard_normal((24, n, n)))
+    sv = np.logspace(0, 3, n)
+    b = ((q * sv) @ q.transpose(0, 2, 1))
+    b = (0.5 * (b + b.transpose(0, 2, 1))).astype(np.float32)
+    g = gp_batch(n, 24, np.float32, seed=3)
+    g["b"] = b
+    g["c"] = (0.01 * g["c"]).astype(np.float32)
+    flat = {k: orc.to_colmajor(v) if v.ndim == 3 else v.reshape(-1) for k, v in g.items()}
+    means, var, info = api.gp_host(n, flat["a"], flat["b"], flat["c"], flat["d"], flat["e"])
+    assert not info.any()
+    om, _ = orc.gp_mean(n, flat["a"], flat["b"], flat["c"], flat["d"])
+    ov, _ = orc.gp_variance(n, flat["a"], flat["b"], flat["c"], flat["e"])
+    m64 = g["b"].astype(np.float64) + np.stack([np.diag(c) for c in g["c"].astype(np.float64)])
+    tm = np.einsum("bi,bi->b", g["a"].astype(np.float64), np.linalg.solve(m64, g["d"].astype(np.float64)[..., None])[..., 0])
+    scale = max(1.0, np.abs(tm).max())
+    e_gpu, e_orc = np.abs(means - tm).max() / scale, np.abs(om - tm).max() / scale
+    print(f"[tc gp128 cond 1e3] gpu {e_gpu:.2e} oracle {e_orc:.2e} (|mean| max {np.abs(tm).max():.2f})")
+    assert e_gpu <= max(1e-4, 4 * e_orc)
+    assert np.abs(var - ov).max() <= max(1e-4, 4 * e_orc) * max(1.0, np.abs(ov).max())
+    # (iii) + (iv): many evaluations, lower triangle of B poisoned
+    batch = 2400
+    gen = torch.Generator(device="cuda").manual_seed(11)
+    r = torch.rand((batch, n, n), generator=gen, device="cuda")
+    bsym = r + r.transpose(1, 2) + n * torch.eye(n, device="cuda")
+    a, c, d = (torch.rand((batch, n), generator=gen, device="cuda") for _ in range(3))
+    e = torch.rand(batch, generator=gen, device="cuda")
+    # column-major storage: element (row r, col c) at [c, r]; poison r > c (the lower triangle)
+    colmajor = bsym.transpose(1, 2).contiguous()
+    poison = torch.tril(torch.ones(n, n, device="cuda"), -1).bool()        # [c, r] with c > r is the UPPER triangle: keep
+    colmajor_p = torch.where(poison.T.unsqueeze(0), torch.full_like(colmajor, float("nan")), colmajor)
+    out_m, out_v = torch.zeros(batch, device="cuda"), torch.zeros(batch, device="cuda")
+    d_info = torch.full((batch,), -1, dtype=torch.int32, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    api.gp_device(n, a.data_ptr(), colmajor_p.data_ptr(), c.data_ptr(), d.data_ptr(), e.data_ptr(), out_m.data_ptr(), out_v.data_ptr(),
+                  batch, np.float32, d_info.data_ptr(), st)
+    torch.cuda.synchronize()
+    assert int(d_info.abs().max()) == 0
+    m64 = bsym.double() + torch.diag_embed(c.double())
+    want_m = (a.double().unsqueeze(1) @ torch.linalg.solve(m64, d.double().unsqueeze(2))).reshape(-1)
+    want_v = e.double() - (a.double().unsqueeze(1) @ torch.linalg.solve(m64, a.double().unsqueeze(2))).reshape(-1)
+    assert float((out_m.double() - want_m).abs().max()) <= 1e-5
+    assert float((out_v.double() - want_v).abs().max()) <= 1e-5
 
 
 # --------------------------------------------------------------------------------------- legacy symbols

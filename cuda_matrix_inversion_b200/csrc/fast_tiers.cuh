@@ -57,6 +57,9 @@ static bool prefer_onesweep() {
     return v == 1;
 }
 
+template <typename T> static bool dense_aligned_any(const StridedIO<T> &io, int n) { return dense_aligned(io, n); }
+template <typename T> static bool dense_aligned_any(const PtrIO<T> &, int) { return false; }
+
 template <typename T, int STAGES>
 static int fast_spd_dense(StridedIO<T> io, int n, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds) {
     if (!dense_aligned(io, n)) return INVGPU_NO_FAST_PATH;
@@ -153,6 +156,11 @@ template <typename IO, typename TT> struct IOCast;
 template <typename T, typename TT> struct IOCast<StridedIO<T>, TT> { typedef StridedIO<TT> type; };
 template <typename T, typename TT> struct IOCast<PtrIO<T>, TT> { typedef PtrIO<TT> type; };
 
+#define INVGPU_GJR_TRY(TT, N, ROWS, MINB)                                                           \
+    if (std::is_same<T, TT>::value && n <= N)                                                        \
+        return launch_gj_roll<TT, N, ROWS, typename IOCast<IO, TT>::type, MINB>(                     \
+            *reinterpret_cast<typename IOCast<IO, TT>::type *>(&io), n, batch, dInfo, st, ds);
+
 // 2-D tile Gauss-Jordan: smallest instantiated padded order >= n wins (ascending lists)
 #define INVGPU_GJT_TRY(TT, N, TR, TC, MINB)                                                         \
     if (std::is_same<T, TT>::value && n <= N)                                                        \
@@ -167,6 +175,7 @@ static int fast_general(IO io, int n, i64 batch, int *dInfo, cudaStream_t st, De
         which = (e && !strcmp(e, "rowlane")) ? 1 : (e && !strcmp(e, "generic")) ? 2 : (e && !strcmp(e, "colsplit")) ? 3 : (e && !strcmp(e, "tile")) ? 4 : 0;
     }
     if (which == 2) return INVGPU_NO_FAST_PATH;
+    const bool use_roll = which == 0 && n <= (sizeof(T) == 4 ? 64 : 32) && !(n == 8 && std::is_same<IO, StridedIO<T>>::value && dense_aligned_any(io, 8));
     if constexpr (std::is_same<IO, StridedIO<T>>::value) {        // dense batches of order exactly 8: one thread per matrix + TMA
         if (which == 0 && n == 8 && dense_aligned(io, 8)) {
 #define INVGPU_GJ8_TRY(TT, NBUF, MINB)                                                               \
@@ -183,6 +192,7 @@ static int fast_general(IO io, int n, i64 batch, int *dInfo, cudaStream_t st, De
             return launch_gj_colsplit<TT, N, CL, WARPS, MINB>(*reinterpret_cast<StridedIO<TT> *>(&io), batch, dInfo, st, ds);
         INVGPU_GJC_ALL(INVGPU_GJC_TRY)
     }
+    if (use_roll) { INVGPU_GJR_ALL(INVGPU_GJR_TRY) }    // rolled lane = row kernel: every n <= 64 that the n = 8 TMA kernel does not take
     if (((which == 0 || which == 3) && n > INVGPU_GJT_MIN_N(T)) || (which == 4 && n > 16)) { INVGPU_GJT_ALL(INVGPU_GJT_TRY) }
     INVGPU_GJ_ALL(INVGPU_GJ_TRY)
     return INVGPU_NO_FAST_PATH;
@@ -240,6 +250,8 @@ static int fast_padded(PadIO<T> io, int tier_n, i64 batch, int *dInfo, cudaStrea
     if (op == 1 && n > INVGPU_GJT_MIN_N(TT) && n <= N && dtype_bytes == (int)sizeof(TT)) return TR * TC <= 32 ? "gj-tile-warp" : "gj-tile-cta";
 #define INVGPU_GJ_NAME(TT, N, ROWS, MINB) \
     if (op == 1 && n <= N && dtype_bytes == (int)sizeof(TT)) return "warp-rowlane";
+#define INVGPU_GJR_NAME(TT, N, ROWS, MINB) \
+    if (op == 1 && n <= N && dtype_bytes == (int)sizeof(TT)) return "warp-rowlane-rolled";
 #define INVGPU_THREAD_BULK_NAME(TT, N, WARPS, MINB) \
     if (op == 0 && n == N && dtype_bytes == (int)sizeof(TT)) return "thread-bulk";
 #define INVGPU_SPD8_NAME(TT, NBUF, MINB) \
@@ -259,6 +271,7 @@ static const char *fast_tier_name(int op, int n, int dtype_bytes) {
     INVGPU_SWEEP_GP_ALL(INVGPU_SWEEP_GP_NAME)
     INVGPU_SPD8_TMA_ALL(INVGPU_GJ8_NAME)
     INVGPU_GJC_ALL(INVGPU_GJC_NAME)
+    INVGPU_GJR_ALL(INVGPU_GJR_NAME)
     INVGPU_GJT_ALL(INVGPU_GJT_NAME)
     INVGPU_GJ_ALL(INVGPU_GJ_NAME)
     INVGPU_TILE_SPD_ALL(INVGPU_TILE_NAME)

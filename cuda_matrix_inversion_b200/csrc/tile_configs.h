@@ -78,6 +78,24 @@
 #define INVGPU_GJ_F64(X) X(double, 8, 1, 4) X(double, 16, INVGPU_GJ16_ROWS_F64, 4) X(double, 32, 1, INVGPU_GJ32_MINB_F64)
 #define INVGPU_GJ_ALL(X) INVGPU_GJ_F32(X) INVGPU_GJ_F64(X)
 
+// lane = row Gauss-Jordan with the ROLLED pivot loop (gj_roll_kernels.cuh: rotating register window, deferred row
+// scaling):  X(T, N, ROWS, MINB); the smallest N >= n serves an order n.  The default general-inverse tier for n <= 64.
+#ifndef INVGPU_GJR64_MINB
+#define INVGPU_GJR64_MINB 2
+#endif
+#ifndef INVGPU_GJR32_ROWS
+#define INVGPU_GJR32_ROWS 1
+#endif
+#ifndef INVGPU_GJR32_MINB
+#define INVGPU_GJR32_MINB 6
+#endif
+#ifndef INVGPU_GJR16_ROWS
+#define INVGPU_GJR16_ROWS 2
+#endif
+#define INVGPU_GJR_F32(X) X(float, 8, 1, 4) X(float, 16, INVGPU_GJR16_ROWS, 6) X(float, 32, INVGPU_GJR32_ROWS, INVGPU_GJR32_MINB) X(float, 64, 2, INVGPU_GJR64_MINB)
+#define INVGPU_GJR_F64(X) X(double, 8, 1, 4) X(double, 16, 2, 4) X(double, 32, 1, 4)
+#define INVGPU_GJR_ALL(X) INVGPU_GJR_F32(X) INVGPU_GJR_F64(X)
+
 // SPD inverse, one-sweep Cholesky (onesweep_kernels.cuh), warp tiers:  X(T, N, TR, TC, STAGE, MINB)
 #ifndef INVGPU_OS_F32_N32_MINB
 #define INVGPU_OS_F32_N32_MINB 5

@@ -393,8 +393,10 @@ def test_gp_128_tensor_core_tier(api, torch):
     e = torch.rand(batch, generator=gen, device="cuda")
     # column-major storage: element (row r, col c) at [c, r]; poison r > c (the lower triangle)
     colmajor = bsym.transpose(1, 2).contiguous()
-    poison = torch.tril(torch.ones(n, n, device="cuda"), -1).bool()        # [c, r] with c > r is the UPPER triangle: keep
-    colmajor_p = torch.where(poison.T.unsqueeze(0), torch.full_like(colmajor, float("nan")), colmajor)
+    ci, ri = torch.arange(n, device="cuda").view(n, 1), torch.arange(n, device="cuda").view(1, n)
+    colmajor_p = colmajor.clone()
+    colmajor_p[:, ri > ci] = float("nan")                                  # [c, r] with r > c: strictly lower triangle
+    assert colmajor_p.is_contiguous() and bool(torch.isnan(colmajor_p[0, 0, 1])) and not bool(torch.isnan(colmajor_p[0, 1, 0]))
     out_m, out_v = torch.zeros(batch, device="cuda"), torch.zeros(batch, device="cuda")
     d_info = torch.full((batch,), -1, dtype=torch.int32, device="cuda")
     st = torch.cuda.current_stream().cuda_stream

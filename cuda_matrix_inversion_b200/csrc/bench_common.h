@@ -10,6 +10,7 @@
  *                   and time it for the *_cpu rows.  Without it those rows are omitted: this
  *                   program has no CPU implementation of its own.
  *   --json          one extra JSON line with throughput and the roofline fraction
+ *   --pageable      keep the GPU calls' host buffers in pageable malloc memory (default: pinned, see bench_buffer)
  *   --dump PATH     write the raw output array of the last algorithm (tests compare runs bit for bit)
  */
 #ifndef INVGPU_BENCH_COMMON_H
@@ -76,8 +77,21 @@ static inline double l1_distance(const float *x, const float *y, size_t count)
     return s;
 }
 
+/* Buffers handed to the *_gpu entry points: pinned host memory from the engine's allocator (DMA'd directly by the host
+ * pipeline, no staging copy; with --gpus N that is what lets the devices' transfers run side by side), pageable malloc
+ * memory when the allocator is unavailable or --pageable is given (what the reference's CLIs pass). */
+void *invgpu_host_alloc(unsigned long long bytes);
+void invgpu_host_free(void *p);
+static inline void *bench_buffer(size_t bytes, bool pageable, bool *pinned)
+{
+    void *p = pageable ? NULL : invgpu_host_alloc(bytes);
+    *pinned = p != NULL;
+    return p ? p : malloc(bytes);
+}
+static inline void bench_buffer_free(void *p, bool pinned) { if (pinned) invgpu_host_free(p); else free(p); }
+
 typedef struct {
-    bool csv, json;
+    bool csv, json, pageable;
     int gpus;
     const char *cpu_lib;
     const char *dump;
@@ -85,10 +99,11 @@ typedef struct {
 
 static inline bench_opts parse_opts(int argc, char const *argv[])
 {
-    bench_opts o = {false, false, 1, NULL, NULL};
+    bench_opts o = {false, false, false, 1, NULL, NULL};
     for (int i = 4; i < argc; ++i) {
         if (!strncmp("-csv", argv[i], 4)) o.csv = true;
         else if (!strcmp("--json", argv[i])) o.json = true;
+        else if (!strcmp("--pageable", argv[i])) o.pageable = true;
         else if (!strcmp("--gpus", argv[i]) && i + 1 < argc) o.gpus = atoi(argv[++i]);
         else if (!strcmp("--cpu-lib", argv[i]) && i + 1 < argc) o.cpu_lib = argv[++i];
         else if (!strcmp("--dump", argv[i]) && i + 1 < argc) o.dump = argv[++i];

@@ -78,11 +78,12 @@ int main(int argc, char const *argv[])
 
     const size_t nv = (size_t)numMatrices * n, nm = (size_t)numMatrices * n * n;
     gp_inputs in;
-    in.a = (Array)malloc(nv * sizeof(float)); in.b = (Array)malloc(nm * sizeof(float));
-    in.c = (Array)malloc(nv * sizeof(float)); in.d = (Array)malloc(nv * sizeof(float));
-    in.e = (Array)malloc((size_t)numMatrices * sizeof(float));
-    Array means_out = (Array)malloc((size_t)numMatrices * sizeof(float));
-    Array variances_out = (Array)malloc((size_t)numMatrices * sizeof(float));
+    bool pin[7];
+    in.a = (Array)bench_buffer(nv * sizeof(float), opt.pageable, &pin[0]); in.b = (Array)bench_buffer(nm * sizeof(float), opt.pageable, &pin[1]);
+    in.c = (Array)bench_buffer(nv * sizeof(float), opt.pageable, &pin[2]); in.d = (Array)bench_buffer(nv * sizeof(float), opt.pageable, &pin[3]);
+    in.e = (Array)bench_buffer((size_t)numMatrices * sizeof(float), opt.pageable, &pin[4]);
+    Array means_out = (Array)bench_buffer((size_t)numMatrices * sizeof(float), opt.pageable, &pin[5]);
+    Array variances_out = (Array)bench_buffer((size_t)numMatrices * sizeof(float), opt.pageable, &pin[6]);
     BENCH_ENSURE(in.a && in.b && in.c && in.d && in.e && means_out && variances_out, "Could not allocate memory");
 #define GP_SETUP()                                                                              \
     do { memcpy(in.a, _a, nv * sizeof(float)); memcpy(in.b, _b, nm * sizeof(float));            \

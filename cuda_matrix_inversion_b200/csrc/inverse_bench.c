@@ -75,8 +75,9 @@ int main(int argc, char const *argv[])
     replicateMatrices(&aInv, n, n, numMatrices, numDuplicates);
     numMatrices *= numDuplicates;
     const size_t total = (size_t)numMatrices * n * n;
-    float *inv = (float *)malloc(total * sizeof(float));
-    float *work = (float *)malloc(total * sizeof(float));
+    bool pin_inv, pin_work;
+    float *inv = (float *)bench_buffer(total * sizeof(float), opt.pageable, &pin_inv);
+    float *work = (float *)bench_buffer(total * sizeof(float), opt.pageable, &pin_work);
     BENCH_ENSURE(inv && work, "Could not allocate the result buffers");
 
     /* optional CPU rows, from a user-supplied build of the reference CPU path */
@@ -127,6 +128,6 @@ int main(int argc, char const *argv[])
         BENCH_ENSURE(f && fwrite(inv, sizeof(float), total, f) == total, "could not write %s", opt.dump);
         fclose(f);
     }
-    free(work); free(inv); free(a); free(aInv);
+    bench_buffer_free(work, pin_work); bench_buffer_free(inv, pin_inv); free(a); free(aInv);
     return 0;
 }

@@ -185,96 +185,136 @@ __device__ __forceinline__ float pivot_rsqrt_newton(float d, int k1, int &bad_at
     return r * fmaf(-0.5f * d * r, r, 1.5f);
 }
 
+// Per-evaluation register state of a row-thread.
+template <int PW>
+struct RowState {
+    float x[PW];                   // the row's entries in the current panel -> its multipliers
+    float ua, ud;                  // right-hand sides a, d of this row (forward substitution in progress)
+    float ya, yd;                  // their finished values (set in the row's own panel)
+    float dself;                   // the row's own diagonal element, kept up to date locally inside its diagonal block
+    int bad_at;
+};
+
 // The warp that owns the diagonal block of a panel (lanes lane0 .. lane0 + PW - 1 = the block's rows; for PW = 16 the
 // other half-warp holds rows below the block, which simply follow as TRSM rows, or finished rows above it, whose
 // registers are don't-cares).  Pivot k:  shfl(dself, pivot lane) -> rsqrt -> l = x_k * r -> dself -= l^2: every lane
 // keeps its OWN diagonal element up to date locally, so the pivot chain never waits for the shared-memory exchange of
 // column k (store l, __syncwarp, broadcast loads, rank-1 tail), which runs beside it.  x[k] becomes the multiplier.
-// Measured alternatives (profiles/r2_tc_gp128_summary.md): starting pivot k+1's shuffle + rsqrt before step k's column
-// loads (-5 %), fetching L(k+1, k) by a fourth shuffle (-13 %: the SM retires one warp shuffle per clock), dropping the
-// Newton step, staggering the CTAs of an SM in time (0 %).
-template <int PW, int K>
+// NM evaluations are advanced TOGETHER: their pivot chains are independent, so one warp interleaves NM dependency
+// chains and shares every __syncwarp / __syncthreads between them (this phase is latency-bound: 54 % of the time line of
+// the single-evaluation kernel, profiles/r2_tc_gp128_summary.md).
+// Measured alternatives: starting pivot k+1's shuffle + rsqrt before step k's column loads (-5 %), fetching L(k+1, k) by a
+// fourth shuffle (-13 %: the SM retires one warp shuffle per clock), staggering the CTAs of an SM in time (0 %).
+template <int PW, int NM, int K>
 struct DiagStep {
-    static __device__ __forceinline__ void run(float (&x)[PW], float &dself, int &bad_at, float &ua, float &ud, float &ya, float &yd,
-                                               GpShared<PW> *sh, int lane, int lane0) {
+    static __device__ __forceinline__ void run(RowState<PW> (&s)[NM], GpShared<PW> *sh, int lane, int lane0) {
         const int pl = lane0 + K;                                 // pivot lane
-        const float r = pivot_rsqrt_newton(__shfl_sync(0xffffffffu, dself, pl), K + 1, bad_at);
-        const float l = x[K] * r;
-        x[K] = l;
-        dself = fmaf(-l, l, dself);
-        const float ta = __shfl_sync(0xffffffffu, ua * r, pl);
-        const float td = __shfl_sync(0xffffffffu, ud * r, pl);
-        if (lane == pl) { ya = ta; yd = td; }
-        ua = fmaf(-l, ta, ua);
-        ud = fmaf(-l, td, ud);
-        if (lane == 0) { sh->rinv[K] = r; sh->ya[K] = ta; sh->yd[K] = td; }
         const int jb = lane - lane0;                              // row inside the block
-        if (jb > K && jb < PW) sh->lcol[K * PW + jb - K - 1] = l; // aligned column: entry i = L11(K + 1 + i, K)
+        float l[NM];
+        #pragma unroll
+        for (int e = 0; e < NM; ++e) {
+            const float r = pivot_rsqrt_newton(__shfl_sync(0xffffffffu, s[e].dself, pl), K + 1, s[e].bad_at);
+            l[e] = s[e].x[K] * r;
+            s[e].x[K] = l[e];
+            s[e].dself = fmaf(-l[e], l[e], s[e].dself);
+            const float ta = __shfl_sync(0xffffffffu, s[e].ua * r, pl);
+            const float td = __shfl_sync(0xffffffffu, s[e].ud * r, pl);
+            if (lane == pl) { s[e].ya = ta; s[e].yd = td; }
+            s[e].ua = fmaf(-l[e], ta, s[e].ua);
+            s[e].ud = fmaf(-l[e], td, s[e].ud);
+            if (lane == 0) { sh[e].rinv[K] = r; sh[e].ya[K] = ta; sh[e].yd[K] = td; }
+            if (jb > K && jb < PW) sh[e].lcol[K * PW + jb - K - 1] = l[e];   // aligned column: entry i = L11(K + 1 + i, K)
+        }
         __syncwarp();
-        rank1_tail<PW, K>(x, l, sh->lcol + K * PW);
-        DiagStep<PW, K + 1>::run(x, dself, bad_at, ua, ud, ya, yd, sh, lane, lane0);
+        Tail<PW, K> tl[NM];
+        #pragma unroll
+        for (int e = 0; e < NM; ++e) tl[e].load(sh[e].lcol + K * PW);
+        #pragma unroll
+        for (int e = 0; e < NM; ++e) tl[e].apply(s[e].x, l[e]);
+        DiagStep<PW, NM, K + 1>::run(s, sh, lane, lane0);
     }
 };
-template <int PW> struct DiagStep<PW, PW> {
-    static __device__ __forceinline__ void run(float (&)[PW], float &, int &, float &, float &, float &, float &, GpShared<PW> *, int, int) {}
+template <int PW, int NM> struct DiagStep<PW, NM, PW> {
+    static __device__ __forceinline__ void run(RowState<PW> (&)[NM], GpShared<PW> *, int, int) {}
 };
 
 // a row below the diagonal block (another warp): l_ik = x_k / L_kk, the row's own rank-1 tail and right-hand sides
-template <int PW, int K>
+template <int PW, int NM, int K>
 struct TrsmStep {
-    static __device__ __forceinline__ void run(float (&x)[PW], float &ua, float &ud, const GpShared<PW> *sh) {
-        const float l = x[K] * sh->rinv[K];
-        x[K] = l;
-        ua = fmaf(-l, sh->ya[K], ua);
-        ud = fmaf(-l, sh->yd[K], ud);
-        rank1_tail<PW, K>(x, l, sh->lcol + K * PW);
-        TrsmStep<PW, K + 1>::run(x, ua, ud, sh);
+    static __device__ __forceinline__ void run(RowState<PW> (&s)[NM], const GpShared<PW> *sh) {
+        float l[NM];
+        Tail<PW, K> tl[NM];
+        #pragma unroll
+        for (int e = 0; e < NM; ++e) {
+            l[e] = s[e].x[K] * sh[e].rinv[K];
+            s[e].x[K] = l[e];
+            s[e].ua = fmaf(-l[e], sh[e].ya[K], s[e].ua);
+            s[e].ud = fmaf(-l[e], sh[e].yd[K], s[e].ud);
+            tl[e].load(sh[e].lcol + K * PW);
+        }
+        #pragma unroll
+        for (int e = 0; e < NM; ++e) tl[e].apply(s[e].x, l[e]);
+        TrsmStep<PW, NM, K + 1>::run(s, sh);
     }
 };
-template <int PW> struct TrsmStep<PW, PW> {
-    static __device__ __forceinline__ void run(float (&)[PW], float &, float &, const GpShared<PW> *) {}
+template <int PW, int NM> struct TrsmStep<PW, NM, PW> {
+    static __device__ __forceinline__ void run(RowState<PW> (&)[NM], const GpShared<PW> *) {}
 };
 
 template <int PW> __device__ __forceinline__ void tmem_ld_panel(uint32_t taddr, float (&x)[PW]);
 template <> __device__ __forceinline__ void tmem_ld_panel<32>(uint32_t taddr, float (&x)[32]) { tmem_ld32(taddr, x); }
 template <> __device__ __forceinline__ void tmem_ld_panel<16>(uint32_t taddr, float (&x)[16]) { tmem_ld16(taddr, x); }
 
-// Fused GP mean / variance, n = 128 fp32, panel width PW (16 or 32).  grid = persistent, block = 128.
-template <int PW, int MINB>
+template <int PW, int NM> struct GpGeoM {
+    static constexpr int PANEL_BYTES = GP_N * PW * 4;            // one operand copy (hi or lo) of one evaluation
+    static constexpr int TMEM_COLS = 128 * NM;
+    static constexpr size_t SMEM_BYTES = (size_t)NM * 2 * PANEL_BYTES + NM * sizeof(GpShared<PW>) + 64;
+};
+
+// Fused GP mean / variance, n = 128 fp32, panel width PW (16 or 32), NM (1 or 2) evaluations per CTA advanced together
+// (evaluation e of the CTA's group lives in TMEM columns 128 e .. 128 e + 127).  grid = persistent, block = 128.
+template <int PW, int NM, int MINB>
 __global__ void __launch_bounds__(128, MINB)
 tc_gp128_kernel(GpIO<float> io, i64 batch, int *__restrict__ info) {
-    using Geo = GpGeo<PW>;
+    using Geo = GpGeoM<PW, NM>;
     constexpr int NP = GP_N / PW;                                 // panels
     // no pointer arithmetic through integers here: the compiler must keep seeing the shared address space (a generic
     // LD.E / ST.E costs ~30 clocks more than LDS / STS, and these accesses sit beside the pivot chain)
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    unsigned char *l_hi = smem_raw, *l_lo = smem_raw + Geo::PANEL_BYTES;
-    GpShared<PW> *sh = reinterpret_cast<GpShared<PW> *>(smem_raw + 2 * Geo::PANEL_BYTES);
+    unsigned char *ops = smem_raw;                                // [NM][hi, lo][PANEL_BYTES]
+    GpShared<PW> *sh = reinterpret_cast<GpShared<PW> *>(smem_raw + NM * 2 * Geo::PANEL_BYTES);
+    uint64_t *mma_done = &sh[0].mma_done;
     const int t = threadIdx.x, w = t >> 5, lane = t & 31;
 
-    if (w == 0) tmem_alloc(&sh->tmem_base, 128);
-    if (t == 0) { mbar_init(&sh->mma_done, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (w == 0) tmem_alloc(&sh[0].tmem_base, Geo::TMEM_COLS);
+    if (t == 0) { mbar_init(mma_done, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = sh->tmem_base;
+    const uint32_t tmem = sh[0].tmem_base;
     const uint32_t my_lane = tmem + ((uint32_t)(32 * w) << 16);           // this warp's 32 TMEM lanes
     uint32_t phase = 0;
     // where this row's multipliers go inside an operand copy (K-major core matrices, see umma_desc_kmajor)
     const uint32_t row_off = (uint32_t)(t >> 3) * 128u + (uint32_t)(t & 7) * 16u;
 
-    for (i64 m = blockIdx.x; m < batch; m += gridDim.x) {
-        const float *__restrict__ brow = io.b + m * (GP_N * GP_N) + (i64)t * GP_N;   // column t == row t of the symmetric input
-        const float cdiag = io.c[m * GP_N + t];
-        float ua = io.a[m * GP_N + t];
-        float ud = io.d ? io.d[m * GP_N + t] : ua;
-        if (t == 0) sh->info = 0;
-        if (m + gridDim.x < batch) {                                          // next evaluation of this CTA: its row prefix -> L2
-            const float *nrow = brow + (i64)gridDim.x * (GP_N * GP_N);
-            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nrow), "r"((uint32_t)(128 * (w + 1))) : "memory");
-        }
-        // ---- load: columns 32c..32c+31 of this row for c <= w (lower triangle), + diag C, into this row's TMEM lane
-        {
+    for (i64 m0 = (i64)blockIdx.x * NM; m0 < batch; m0 += (i64)gridDim.x * NM) {
+        RowState<PW> s[NM];
+        i64 mm[NM];
+        #pragma unroll
+        for (int e = 0; e < NM; ++e) {
+            mm[e] = (m0 + e < batch) ? m0 + e : batch - 1;                    // a ragged last group recomputes the last evaluation
+            const i64 m = mm[e];
+            const float *__restrict__ brow = io.b + m * (GP_N * GP_N) + (i64)t * GP_N;   // column t == row t of the symmetric input
+            const float cdiag = io.c[m * GP_N + t];
+            s[e].ua = io.a[m * GP_N + t];
+            s[e].ud = io.d ? io.d[m * GP_N + t] : s[e].ua;
+            s[e].ya = 0.f; s[e].yd = 0.f; s[e].bad_at = 0; s[e].dself = 0.f;
+            if (t == 0) sh[e].info = 0;
+            if (m + (i64)gridDim.x * NM < batch) {                            // this slot's next evaluation: its row prefix -> L2
+                const float *nrow = brow + (i64)gridDim.x * NM * (GP_N * GP_N);
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nrow), "r"((uint32_t)(128 * (w + 1))) : "memory");
+            }
+            // ---- load: columns 32c..32c+31 of this row for c <= w (lower triangle), + diag C, into this row's TMEM lane
             float v32[32];
             #pragma unroll
             for (int c = 0; c < 4; ++c) {
@@ -288,43 +328,51 @@ tc_gp128_kernel(GpIO<float> io, i64 batch, int *__restrict__ info) {
                         #pragma unroll
                         for (int j = 0; j < 32; ++j) if (j == lane) v32[j] += cdiag;
                     }
-                    tmem_st32(my_lane + 32 * c, v32);
+                    tmem_st32(my_lane + 128 * e + 32 * c, v32);
                 }
             }
-            tmem_st_wait();
         }
-        float ya = 0.f, yd = 0.f;
+        tmem_st_wait();
 
         #pragma unroll 1
         for (int p = 0; p < NP; ++p) {
             const int wd = (p * PW) >> 5;                                     // the warp that owns the diagonal block
             const int lane0 = (p * PW) & 31;                                  // its first lane
-            float x[PW];
             if (w >= wd) {
-                if (p > 0) { mbar_wait(&sh->mma_done, phase); tc_fence_after(); }   // the update of panel p-1 has landed
-                tmem_ld_panel<PW>(my_lane + PW * p, x);
+                if (p > 0) { mbar_wait(mma_done, phase); tc_fence_after(); }  // the updates of panel p-1 have landed
+                #pragma unroll
+                for (int e = 0; e < NM; ++e) tmem_ld_panel<PW>(my_lane + 128 * e + PW * p, s[e].x);
             }
             if (p > 0) phase ^= 1;                                            // every thread tracks the barrier's phase
             if (w == wd) {
-                float dself = 0.f;                                            // this lane's own diagonal element
                 #pragma unroll
-                for (int j = 0; j < PW; ++j) dself = (lane - lane0 == j) ? x[j] : dself;
-                int bad_at = 0;
-                DiagStep<PW, 0>::run(x, dself, bad_at, ua, ud, ya, yd, sh, lane, lane0);
-                if (lane == 0 && bad_at != 0 && sh->info == 0) sh->info = p * PW + bad_at;
+                for (int e = 0; e < NM; ++e) {
+                    float dself = 0.f;                                        // this lane's own diagonal element
+                    #pragma unroll
+                    for (int j = 0; j < PW; ++j) dself = (lane - lane0 == j) ? s[e].x[j] : dself;
+                    s[e].dself = dself; s[e].bad_at = 0;
+                }
+                DiagStep<PW, NM, 0>::run(s, sh, lane, lane0);
+                #pragma unroll
+                for (int e = 0; e < NM; ++e)
+                    if (lane == 0 && s[e].bad_at != 0 && sh[e].info == 0) sh[e].info = p * PW + s[e].bad_at;
             }
             __syncthreads();
-            if (w > wd) TrsmStep<PW, 0>::run(x, ua, ud, sh);
-            if (w >= wd && p < NP - 1) {                                      // publish the row's multipliers as hi + lo
+            if (w > wd) TrsmStep<PW, NM, 0>::run(s, sh);
+            if (w >= wd && p < NP - 1) {                                      // publish the rows' multipliers as hi + lo
                 #pragma unroll
-                for (int c = 0; c < PW / 4; ++c) {
-                    float4 hi, lo;
-                    hi.x = __uint_as_float(__float_as_uint(x[4 * c + 0]) & 0xffffe000u); lo.x = x[4 * c + 0] - hi.x;
-                    hi.y = __uint_as_float(__float_as_uint(x[4 * c + 1]) & 0xffffe000u); lo.y = x[4 * c + 1] - hi.y;
-                    hi.z = __uint_as_float(__float_as_uint(x[4 * c + 2]) & 0xffffe000u); lo.z = x[4 * c + 2] - hi.z;
-                    hi.w = __uint_as_float(__float_as_uint(x[4 * c + 3]) & 0xffffe000u); lo.w = x[4 * c + 3] - hi.w;
-                    *reinterpret_cast<float4 *>(l_hi + c * GP_CHUNK_STRIDE + row_off) = hi;
-                    *reinterpret_cast<float4 *>(l_lo + c * GP_CHUNK_STRIDE + row_off) = lo;
+                for (int e = 0; e < NM; ++e) {
+                    unsigned char *l_hi = ops + (size_t)(2 * e) * Geo::PANEL_BYTES, *l_lo = l_hi + Geo::PANEL_BYTES;
+                    #pragma unroll
+                    for (int c = 0; c < PW / 4; ++c) {
+                        float4 hi, lo;
+                        hi.x = __uint_as_float(__float_as_uint(s[e].x[4 * c + 0]) & 0xffffe000u); lo.x = s[e].x[4 * c + 0] - hi.x;
+                        hi.y = __uint_as_float(__float_as_uint(s[e].x[4 * c + 1]) & 0xffffe000u); lo.y = s[e].x[4 * c + 1] - hi.y;
+                        hi.z = __uint_as_float(__float_as_uint(s[e].x[4 * c + 2]) & 0xffffe000u); lo.z = s[e].x[4 * c + 2] - hi.z;
+                        hi.w = __uint_as_float(__float_as_uint(s[e].x[4 * c + 3]) & 0xffffe000u); lo.w = s[e].x[4 * c + 3] - hi.w;
+                        *reinterpret_cast<float4 *>(l_hi + c * GP_CHUNK_STRIDE + row_off) = hi;
+                        *reinterpret_cast<float4 *>(l_lo + c * GP_CHUNK_STRIDE + row_off) = lo;
+                    }
                 }
                 fence_async_smem();                                           // generic-proxy writes -> visible to the tensor core
             }
@@ -334,41 +382,50 @@ tc_gp128_kernel(GpIO<float> io, i64 batch, int *__restrict__ info) {
                 tc_fence_after();
                 const int n_cols = GP_N - PW * (p + 1);
                 const uint32_t idesc = umma_idesc_tf32(128, n_cols, true);
-                const uint32_t d_addr = tmem + PW * (p + 1);
                 const uint32_t b_rows = (uint32_t)(PW * (p + 1) / 8) * 128u;   // B operand = rows PW(p+1).. of the same panel
                 #pragma unroll
-                for (int ks = 0; ks < PW / 8; ++ks) {
-                    const uint32_t koff = (uint32_t)ks * 2u * GP_CHUNK_STRIDE;
-                    const uint64_t a_hi = umma_desc_kmajor(smem_addr(l_hi) + koff, GP_CHUNK_STRIDE, 128);
-                    const uint64_t a_lo = umma_desc_kmajor(smem_addr(l_lo) + koff, GP_CHUNK_STRIDE, 128);
-                    const uint64_t b_hi = umma_desc_kmajor(smem_addr(l_hi) + koff + b_rows, GP_CHUNK_STRIDE, 128);
-                    const uint64_t b_lo = umma_desc_kmajor(smem_addr(l_lo) + koff + b_rows, GP_CHUNK_STRIDE, 128);
-                    umma_tf32(d_addr, a_lo, b_hi, idesc, 1u);                 // small terms first
-                    umma_tf32(d_addr, a_hi, b_lo, idesc, 1u);
-                    umma_tf32(d_addr, a_hi, b_hi, idesc, 1u);
+                for (int e = 0; e < NM; ++e) {
+                    const uint32_t d_addr = tmem + 128 * e + PW * (p + 1);
+                    const uint32_t s_hi = smem_addr(ops + (size_t)(2 * e) * Geo::PANEL_BYTES), s_lo = s_hi + Geo::PANEL_BYTES;
+                    #pragma unroll
+                    for (int ks = 0; ks < PW / 8; ++ks) {
+                        const uint32_t koff = (uint32_t)ks * 2u * GP_CHUNK_STRIDE;
+                        const uint64_t a_hi = umma_desc_kmajor(s_hi + koff, GP_CHUNK_STRIDE, 128);
+                        const uint64_t a_lo = umma_desc_kmajor(s_lo + koff, GP_CHUNK_STRIDE, 128);
+                        const uint64_t b_hi = umma_desc_kmajor(s_hi + koff + b_rows, GP_CHUNK_STRIDE, 128);
+                        const uint64_t b_lo = umma_desc_kmajor(s_lo + koff + b_rows, GP_CHUNK_STRIDE, 128);
+                        umma_tf32(d_addr, a_lo, b_hi, idesc, 1u);             // small terms first
+                        umma_tf32(d_addr, a_hi, b_lo, idesc, 1u);
+                        umma_tf32(d_addr, a_hi, b_hi, idesc, 1u);
+                    }
                 }
-                umma_commit(&sh->mma_done);
+                umma_commit(mma_done);
             }
         }
         // ---- epilogue: means = sum ya*yd, variances = E - sum ya^2 (every row finalised its y in its own panel)
-        float pm = ya * yd, pq = ya * ya;
         #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { pm += __shfl_xor_sync(0xffffffffu, pm, o); pq += __shfl_xor_sync(0xffffffffu, pq, o); }
-        if (lane == 0) { sh->red[w] = pm; sh->red[4 + w] = pq; }
+        for (int e = 0; e < NM; ++e) {
+            float pm = s[e].ya * s[e].yd, pq = s[e].ya * s[e].ya;
+            #pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { pm += __shfl_xor_sync(0xffffffffu, pm, o); pq += __shfl_xor_sync(0xffffffffu, pq, o); }
+            if (lane == 0) { sh[e].red[w] = pm; sh[e].red[4 + w] = pq; }
+        }
         __syncthreads();
-        if (t == 0) {
-            const int st = sh->info;
-            const float sm = (sh->red[0] + sh->red[1]) + (sh->red[2] + sh->red[3]);
-            const float sq = (sh->red[4] + sh->red[5]) + (sh->red[6] + sh->red[7]);
+        if (t < NM && m0 + t < batch) {
+            const GpShared<PW> &r = sh[t];
+            const i64 m = m0 + t;
+            const int st = r.info;
+            const float sm = (r.red[0] + r.red[1]) + (r.red[2] + r.red[3]);
+            const float sq = (r.red[4] + r.red[5]) + (r.red[6] + r.red[7]);
             if (info) info[m] = st;
             if (io.means) io.means[m] = st ? dev_nan<float>() : sm;
             if (io.variances) io.variances[m] = st ? dev_nan<float>() : io.e[m] - sq;
         }
-        __syncthreads();                                                     // red / info reuse; all tensor-core work of this matrix is done
+        __syncthreads();                                                     // red / info reuse; all tensor-core work of this group is done
     }
     tc_fence_before();
     __syncthreads();
-    if (w == 0) tmem_dealloc(tmem, 128);
+    if (w == 0) tmem_dealloc(tmem, Geo::TMEM_COLS);
 }
 
 }  // namespace tc

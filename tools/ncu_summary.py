@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Turn an .ncu-rep (read here, no GPU needed) into the markdown summary kept under profiles/.
-   python tools/ncu_summary.py gpurun_out/tile32_r1.ncu-rep profiles/r1_tile32_summary.md [launches.csv]"""
+   python tools/ncu_summary.py gpurun_out/tile32_r1.ncu-rep profiles/r1_tile32_summary.md [launches.csv] [--note "batch ..., command ..."]
+The note records the workload (batch, command line) so that traffic vs algorithmic bytes can be recomputed from the summary."""
 import collections
 import csv
 import io
@@ -15,6 +16,11 @@ def raw(rep):
 
 
 def main():
+    note = None
+    if "--note" in sys.argv:
+        i = sys.argv.index("--note")
+        note = sys.argv[i + 1]
+        del sys.argv[i:i + 2]
     rep, dst = sys.argv[1], sys.argv[2]
     hdr, units, vals = raw(rep)
     get = {h: (v, u) for h, v, u in zip(hdr, vals, units)}
@@ -28,7 +34,10 @@ def main():
         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
         "smsp__inst_executed.sum", "sm__cycles_elapsed.avg",
     ]
-    lines = [f"# ncu summary of `{rep}`", "", "| metric | value | unit |", "|---|---|---|"]
+    lines = [f"# ncu summary of `{rep}`", ""]
+    if note:
+        lines += [f"Workload: {note}", ""]
+    lines += ["| metric | value | unit |", "|---|---|---|"]
     for k in keys:
         if k in get:
             lines.append(f"| {k} | {get[k][0]} | {get[k][1]} |")

@@ -484,7 +484,12 @@ static int run_mixed_spd(T *const *hIn, T *const *hOut, const int *hN, i64 count
     const auto t_plan0 = std::chrono::steady_clock::now();
     // counting sort by n, descending inside each tier: two passes over the batch, no comparisons; both passes are
     // split over a few host threads (per-thread histograms give every thread its own output ranges)
-    const int nthr = (count >= (1 << 16)) ? (int)std::min<unsigned>(8, std::max(1u, std::thread::hardware_concurrency())) : 1;
+    // planner threads: a share of the host cores -- with one process per GPU (bench.py under torchrun: 8 ranks on 32 cores)
+    // every rank plans at the same time, so each takes cores / visible devices, at most 8
+    int ndev = 1;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) { cudaGetLastError(); ndev = 1; }
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const int nthr = (count >= (1 << 16)) ? (int)std::min<unsigned>(8, std::max(1u, hw / (unsigned)ndev)) : 1;
     std::vector<std::array<i64, 257>> thist(nthr);
     std::atomic<int> bad_arg{0};
     auto slice = [&](int t, i64 &b, i64 &e) { b = count * t / nthr; e = count * (t + 1) / nthr; };

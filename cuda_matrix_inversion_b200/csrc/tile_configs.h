@@ -164,8 +164,24 @@
 // mixed-dimension batches on the sweep kernel with the padded IO policy:  X(T, N, TR, TC, MINB); tiers in ascending N
 // (intermediate tiers 24 / 48 / 96 / 192 on square grids: their strictly-upper 4x4 blocks are never materialised, so a
 //  12 x 12 tile costs 96 registers; they cut the (N / n)^3 padding waste of a tier from 3.0 to 1.7 on average)
+#ifndef INVGPU_PAD256_TR
+#define INVGPU_PAD256_TR 16
+#define INVGPU_PAD256_TC 16
+#define INVGPU_PAD256_MINB 1
+#endif
+#ifndef INVGPU_PAD192_TR
+#define INVGPU_PAD192_TR 16
+#define INVGPU_PAD192_TC 16
+#define INVGPU_PAD192_MINB 1
+#endif
+#ifndef INVGPU_PAD128_TR
+#define INVGPU_PAD128_TR 8
+#define INVGPU_PAD128_TC 8
+#define INVGPU_PAD128_MINB 2
+#endif
 #define INVGPU_SWEEP_PAD_F32(X) X(float, 16, 2, 2, 4) X(float, 24, 2, 2, 3) X(float, 32, 2, 4, 3) X(float, 48, 4, 4, 3) X(float, 64, 4, 4, 2) \
-    X(float, 96, 8, 8, 4) X(float, 128, 8, 8, 2) X(float, 192, 16, 16, 1) X(float, 256, 16, 16, 1)
+    X(float, 96, 8, 8, 4) X(float, 128, INVGPU_PAD128_TR, INVGPU_PAD128_TC, INVGPU_PAD128_MINB) \
+    X(float, 192, INVGPU_PAD192_TR, INVGPU_PAD192_TC, INVGPU_PAD192_MINB) X(float, 256, INVGPU_PAD256_TR, INVGPU_PAD256_TC, INVGPU_PAD256_MINB)
 #define INVGPU_SWEEP_PAD_F64(X) X(double, 16, 2, 2, 2) X(double, 32, 4, 4, 2) X(double, 64, 8, 8, 4) X(double, 128, 16, 16, 1)
 #define INVGPU_SWEEP_PAD_ALL(X) INVGPU_SWEEP_PAD_F32(X) INVGPU_SWEEP_PAD_F64(X)
 

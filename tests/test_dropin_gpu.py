@@ -124,6 +124,11 @@ def test_reference_gauss_bench_relinked_against_libinvgpu():
 
 # ------------------------------------------------------------------ CLI: --gpus N, detailed logging
 def test_inverse_bench_two_gpus_bit_identical_and_faster(api, tmp_path):
+    """`bin/inverse_bench --gpus 2`: one host thread per device, each through its own device's pipeline (per-device engine
+    lock).  Output bit-identical to --gpus 1, and the two devices really run side by side: the speed-up must reach 85 % of what
+    the BOX allows for two concurrent host<->device streams -- measured on the spot with the copy-only probe
+    (tools/bin/xfer_bench, `pipeline` rows; 1.77x on the pool's 2-GPU boxes, only 1.2x on its 8-GPU boxes, whose aggregate
+    host path saturates near 105-130 GB/s: profiles/r2_xfer_*.csv)."""
     if api.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     d = os.path.join(FIX, "inverse_100_32x32")
@@ -136,8 +141,18 @@ def test_inverse_bench_two_gpus_bit_identical_and_faster(api, tmp_path):
     b = np.fromfile(tmp_path / "inv2.bin", dtype=np.float32)
     assert a.size == 50000 * 32 * 32 and np.array_equal(a, b)             # same kernels, disjoint shards: bit-identical
     rate = {g: float(re.search(r'"inversions_per_s": ([-+.e\d]+)', outs[g]).group(1)) for g in (1, 2)}
-    print(f"[--gpus] 1 GPU {rate[1]:.3e} inv/s, 2 GPUs {rate[2]:.3e} inv/s ({rate[2] / rate[1]:.2f}x)")
-    assert rate[2] >= 1.6 * rate[1]
+    xb = _run(os.path.join(ROOT, "tools", "bin", "xfer_bench"), "--gpus", "2", "--quick", "--mb", "512")
+    assert xb.returncode == 0, xb.stderr
+    ceil = {}
+    for ln in xb.stdout.splitlines():
+        f = ln.split(",")
+        if len(f) == 8 and f[4] == "pipeline" and f[2] == "1":
+            ceil[int(f[0])] = float(f[7])
+    allowed = ceil[2] / ceil[1]
+    print(f"[--gpus] 1 GPU {rate[1]:.3e} inv/s, 2 GPUs {rate[2]:.3e} inv/s ({rate[2] / rate[1]:.2f}x); the box's copy-only pipeline: "
+          f"{ceil[1]:.1f} -> {ceil[2]:.1f} GB/s ({allowed:.2f}x)")
+    assert rate[2] / rate[1] >= 0.85 * allowed
+    assert rate[2] / rate[1] >= 1.05                                       # and never serialised
 
 
 def test_detailed_logging_phase_lines():

@@ -26,6 +26,9 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#ifndef INVGPU_TC_EXP
+#define INVGPU_TC_EXP 0      // timing experiments only (results are wrong when non-zero): 1 = no right-hand sides in the diagonal block, 2 = no rinv / y stores, 4 = no Newton step, 8 = no rank-1 tail in the diagonal block
+#endif
 #include <stdint.h>
 
 #include "common.cuh"
@@ -182,7 +185,11 @@ __device__ __forceinline__ float pivot_rsqrt_newton(float d, int k1, int &bad_at
     d = bad ? 1.f : d;
     float r;
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
+#if INVGPU_TC_EXP & 4
+    return r;
+#else
     return r * fmaf(-0.5f * d * r, r, 1.5f);
+#endif
 }
 
 // Per-evaluation register state of a row-thread.
@@ -217,20 +224,28 @@ struct DiagStep {
             l[e] = s[e].x[K] * r;
             s[e].x[K] = l[e];
             s[e].dself = fmaf(-l[e], l[e], s[e].dself);
+#if !(INVGPU_TC_EXP & 1)
             const float ta = __shfl_sync(0xffffffffu, s[e].ua * r, pl);
             const float td = __shfl_sync(0xffffffffu, s[e].ud * r, pl);
             if (lane == pl) { s[e].ya = ta; s[e].yd = td; }
             s[e].ua = fmaf(-l[e], ta, s[e].ua);
             s[e].ud = fmaf(-l[e], td, s[e].ud);
+#else
+            const float ta = r, td = r;
+#endif
+#if !(INVGPU_TC_EXP & 2)
             if (lane == 0) { sh[e].rinv[K] = r; sh[e].ya[K] = ta; sh[e].yd[K] = td; }
+#endif
             if (jb > K && jb < PW) sh[e].lcol[K * PW + jb - K - 1] = l[e];   // aligned column: entry i = L11(K + 1 + i, K)
         }
         __syncwarp();
         Tail<PW, K> tl[NM];
         #pragma unroll
         for (int e = 0; e < NM; ++e) tl[e].load(sh[e].lcol + K * PW);
+#if !(INVGPU_TC_EXP & 8)
         #pragma unroll
         for (int e = 0; e < NM; ++e) tl[e].apply(s[e].x, l[e]);
+#endif
         DiagStep<PW, NM, K + 1>::run(s, sh, lane, lane0);
     }
 };

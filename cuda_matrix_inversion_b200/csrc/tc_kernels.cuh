@@ -26,9 +26,10 @@
 #pragma once
 
 #include <cuda_runtime.h>
-#ifndef INVGPU_TC_EXP
-#define INVGPU_TC_EXP 0      // timing experiments only (results are wrong when non-zero): 1 = no right-hand sides in the diagonal block, 2 = no rinv / y stores, 4 = no Newton step, 8 = no rank-1 tail in the diagonal block
+#ifndef INVGPU_TC_STAGE
+#define INVGPU_TC_STAGE 0
 #endif
+
 #include <stdint.h>
 
 #include "common.cuh"
@@ -53,6 +54,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     }
 }
 
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+// 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier (bytes: multiple of 16, both sides 16-byte aligned)
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
 __device__ __forceinline__ void tmem_alloc(uint32_t *slot, uint32_t cols) {      // one full warp
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(slot)), "r"(cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -140,6 +149,7 @@ struct __align__(16) GpShared {
     float ya[PW], yd[PW];          // forward-substituted right-hand sides of the current panel
     float red[2 * 4];
     uint64_t mma_done;
+    uint64_t stage_full;           // the staged chunk of the next evaluation has landed (bulk copies, complete_tx)
     uint32_t tmem_base;
     int info;
 };
@@ -185,11 +195,7 @@ __device__ __forceinline__ float pivot_rsqrt_newton(float d, int k1, int &bad_at
     d = bad ? 1.f : d;
     float r;
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
-#if INVGPU_TC_EXP & 4
-    return r;
-#else
     return r * fmaf(-0.5f * d * r, r, 1.5f);
-#endif
 }
 
 // Per-evaluation register state of a row-thread.
@@ -199,6 +205,7 @@ struct RowState {
     float ua, ud;                  // right-hand sides a, d of this row (forward substitution in progress)
     float ya, yd;                  // their finished values (set in the row's own panel)
     float dself;                   // the row's own diagonal element, kept up to date locally inside its diagonal block
+    float rkeep;                   // 1 / L_kk of the row's own pivot (kept by the pivot lane, stored once per block)
     int bad_at;
 };
 
@@ -224,28 +231,15 @@ struct DiagStep {
             l[e] = s[e].x[K] * r;
             s[e].x[K] = l[e];
             s[e].dself = fmaf(-l[e], l[e], s[e].dself);
-#if !(INVGPU_TC_EXP & 1)
-            const float ta = __shfl_sync(0xffffffffu, s[e].ua * r, pl);
-            const float td = __shfl_sync(0xffffffffu, s[e].ud * r, pl);
-            if (lane == pl) { s[e].ya = ta; s[e].yd = td; }
-            s[e].ua = fmaf(-l[e], ta, s[e].ua);
-            s[e].ud = fmaf(-l[e], td, s[e].ud);
-#else
-            const float ta = r, td = r;
-#endif
-#if !(INVGPU_TC_EXP & 2)
-            if (lane == 0) { sh[e].rinv[K] = r; sh[e].ya[K] = ta; sh[e].yd[K] = td; }
-#endif
+            s[e].rkeep = (lane == pl) ? r : s[e].rkeep;                      // one store per block instead of one per pivot
             if (jb > K && jb < PW) sh[e].lcol[K * PW + jb - K - 1] = l[e];   // aligned column: entry i = L11(K + 1 + i, K)
         }
         __syncwarp();
         Tail<PW, K> tl[NM];
         #pragma unroll
         for (int e = 0; e < NM; ++e) tl[e].load(sh[e].lcol + K * PW);
-#if !(INVGPU_TC_EXP & 8)
         #pragma unroll
         for (int e = 0; e < NM; ++e) tl[e].apply(s[e].x, l[e]);
-#endif
         DiagStep<PW, NM, K + 1>::run(s, sh, lane, lane0);
     }
 };
@@ -253,7 +247,32 @@ template <int PW, int NM> struct DiagStep<PW, NM, PW> {
     static __device__ __forceinline__ void run(RowState<PW> (&)[NM], GpShared<PW> *, int, int) {}
 };
 
-// a row below the diagonal block (another warp): l_ik = x_k / L_kk, the row's own rank-1 tail and right-hand sides
+// Forward substitution of both right-hand sides through the diagonal block, by the warp that owns it, AFTER the block is
+// factored and WHILE the other warps run their row TRSMs (this warp has no TRSM rows): y_k = u_k / L_kk in the pivot lane,
+// broadcast by shuffle, u_i -= L_ik y_k in the rows below it (x[K] is the lane's multiplier).  Inside the pivot loop these
+// two shuffles stalled every step of the in-order pivot chain: 18 % of the kernel (timing experiment, r2_tc_gp128_summary.md).
+template <int PW, int NM, int K>
+struct DiagRhsStep {
+    static __device__ __forceinline__ void run(RowState<PW> (&s)[NM], GpShared<PW> *sh, int lane, int lane0) {
+        const int pl = lane0 + K;
+        #pragma unroll
+        for (int e = 0; e < NM; ++e) {
+            const float r = sh[e].rinv[K];
+            const float ta = __shfl_sync(0xffffffffu, s[e].ua * r, pl);
+            const float td = __shfl_sync(0xffffffffu, s[e].ud * r, pl);
+            s[e].ya = (lane == pl) ? ta : s[e].ya;
+            s[e].yd = (lane == pl) ? td : s[e].yd;
+            s[e].ua = fmaf(-s[e].x[K], ta, s[e].ua);
+            s[e].ud = fmaf(-s[e].x[K], td, s[e].ud);
+        }
+        DiagRhsStep<PW, NM, K + 1>::run(s, sh, lane, lane0);
+    }
+};
+template <int PW, int NM> struct DiagRhsStep<PW, NM, PW> {
+    static __device__ __forceinline__ void run(RowState<PW> (&)[NM], GpShared<PW> *, int, int) {}
+};
+
+// a row below the diagonal block (another warp): l_ik = x_k / L_kk and the row's own rank-1 tail
 template <int PW, int NM, int K>
 struct TrsmStep {
     static __device__ __forceinline__ void run(RowState<PW> (&s)[NM], const GpShared<PW> *sh) {
@@ -261,10 +280,8 @@ struct TrsmStep {
         Tail<PW, K> tl[NM];
         #pragma unroll
         for (int e = 0; e < NM; ++e) {
-            l[e] = s[e].x[K] * sh[e].rinv[K];
+            l[e] = s[e].x[K] * sh[e].rinv[K];                              // (the compiler merges these into 128-bit broadcast loads)
             s[e].x[K] = l[e];
-            s[e].ua = fmaf(-l[e], sh[e].ya[K], s[e].ua);
-            s[e].ud = fmaf(-l[e], sh[e].yd[K], s[e].ud);
             tl[e].load(sh[e].lcol + K * PW);
         }
         #pragma unroll
@@ -276,6 +293,19 @@ template <int PW, int NM> struct TrsmStep<PW, NM, PW> {
     static __device__ __forceinline__ void run(RowState<PW> (&)[NM], const GpShared<PW> *) {}
 };
 
+// the right-hand sides of a row below the block, once the block's y are known: u_i -= sum_k L_ik y_k
+template <int PW>
+__device__ __forceinline__ void rhs_row_update(RowState<PW> &s, const GpShared<PW> &sh) {
+    #pragma unroll
+    for (int c = 0; c < PW / 4; ++c) {
+        const float4 a = reinterpret_cast<const float4 *>(sh.ya)[c], d = reinterpret_cast<const float4 *>(sh.yd)[c];
+        s.ua = fmaf(-s.x[4 * c + 0], a.x, s.ua); s.ud = fmaf(-s.x[4 * c + 0], d.x, s.ud);
+        s.ua = fmaf(-s.x[4 * c + 1], a.y, s.ua); s.ud = fmaf(-s.x[4 * c + 1], d.y, s.ud);
+        s.ua = fmaf(-s.x[4 * c + 2], a.z, s.ua); s.ud = fmaf(-s.x[4 * c + 2], d.z, s.ud);
+        s.ua = fmaf(-s.x[4 * c + 3], a.w, s.ua); s.ud = fmaf(-s.x[4 * c + 3], d.w, s.ud);
+    }
+}
+
 template <int PW> __device__ __forceinline__ void tmem_ld_panel(uint32_t taddr, float (&x)[PW]);
 template <> __device__ __forceinline__ void tmem_ld_panel<32>(uint32_t taddr, float (&x)[32]) { tmem_ld32(taddr, x); }
 template <> __device__ __forceinline__ void tmem_ld_panel<16>(uint32_t taddr, float (&x)[16]) { tmem_ld16(taddr, x); }
@@ -283,7 +313,13 @@ template <> __device__ __forceinline__ void tmem_ld_panel<16>(uint32_t taddr, fl
 template <int PW, int NM> struct GpGeoM {
     static constexpr int PANEL_BYTES = GP_N * PW * 4;            // one operand copy (hi or lo) of one evaluation
     static constexpr int TMEM_COLS = 128 * NM;
-    static constexpr size_t SMEM_BYTES = (size_t)NM * 2 * PANEL_BYTES + NM * sizeof(GpShared<PW>) + 64;
+    // next evaluation staged through shared memory, chunk by chunk, while the current one is factored (INVGPU_TC_STAGE=1 at
+    // build time).  Measured: 9.56 ms vs 8.43 ms without it (200 000 evaluations) -- the kernel is bound by the SM's shared-
+    // memory / LSU data pipe (63 % busy, profiles/r2_tc_gp128_summary.md), and the stage adds traffic there; off by default.
+    static constexpr bool STAGED = (INVGPU_TC_STAGE != 0 && NM == 1 && PW == 16);
+    static constexpr int STAGE_STRIDE = 144;                     // bytes per staged row: 128 + 16 (conflict-free 128-bit reads)
+    static constexpr int STAGE_BYTES = STAGED ? GP_N * STAGE_STRIDE : 0;
+    static constexpr size_t SMEM_BYTES = (size_t)NM * 2 * PANEL_BYTES + STAGE_BYTES + NM * sizeof(GpShared<PW>) + 64;
 };
 
 // Fused GP mean / variance, n = 128 fp32, panel width PW (16 or 32), NM (1 or 2) evaluations per CTA advanced together
@@ -297,7 +333,7 @@ tc_gp128_kernel(GpIO<float> io, i64 batch, int *__restrict__ info) {
     // LD.E / ST.E costs ~30 clocks more than LDS / STS, and these accesses sit beside the pivot chain)
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char *ops = smem_raw;                                // [NM][hi, lo][PANEL_BYTES]
-    GpShared<PW> *sh = reinterpret_cast<GpShared<PW> *>(smem_raw + NM * 2 * Geo::PANEL_BYTES);
+    GpShared<PW> *sh = reinterpret_cast<GpShared<PW> *>(smem_raw + NM * 2 * Geo::PANEL_BYTES + Geo::STAGE_BYTES);
     uint64_t *mma_done = &sh[0].mma_done;
     const int t = threadIdx.x, w = t >> 5, lane = t & 31;
 
@@ -312,6 +348,19 @@ tc_gp128_kernel(GpIO<float> io, i64 batch, int *__restrict__ info) {
     // where this row's multipliers go inside an operand copy (K-major core matrices, see umma_desc_kmajor)
     const uint32_t row_off = (uint32_t)(t >> 3) * 128u + (uint32_t)(t & 7) * 16u;
 
+    // STAGED (one evaluation per CTA, PW = 16): chunk c (columns 32c..32c+31) of the NEXT evaluation is fetched while the
+    // current one is still being factored.  Once the two panels covering those columns are done no MMA touches them again,
+    // so the TMEM cells are free: right after that panel's first barrier every row that needs the chunk issues ONE 128-byte
+    // bulk copy (cp.async.bulk, no registers, no warp waits) into a shared-memory stage; a panel later the rows move their
+    // 32 values stage -> registers -> TMEM.  Only the very first evaluation of a CTA is loaded up front (the load phase is
+    // 24 % of a CTA's time line).  Measured slower than loading up front (see GpGeoM::STAGED), like fetching through registers
+    // (9.70 ms): four CTAs per SM already hide each other's load phases, and the SM-level bound is the LSU data pipe.
+    constexpr bool STAGED = Geo::STAGED;
+    unsigned char *stage = smem_raw + NM * 2 * Geo::PANEL_BYTES;
+    bool prefetched = false;
+    uint32_t stage_phase = 0;
+    if (STAGED && t == 0) { mbar_init(&sh[0].stage_full, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (STAGED) __syncthreads();
     for (i64 m0 = (i64)blockIdx.x * NM; m0 < batch; m0 += (i64)gridDim.x * NM) {
         RowState<PW> s[NM];
         i64 mm[NM];
@@ -320,15 +369,12 @@ tc_gp128_kernel(GpIO<float> io, i64 batch, int *__restrict__ info) {
             mm[e] = (m0 + e < batch) ? m0 + e : batch - 1;                    // a ragged last group recomputes the last evaluation
             const i64 m = mm[e];
             const float *__restrict__ brow = io.b + m * (GP_N * GP_N) + (i64)t * GP_N;   // column t == row t of the symmetric input
-            const float cdiag = io.c[m * GP_N + t];
             s[e].ua = io.a[m * GP_N + t];
             s[e].ud = io.d ? io.d[m * GP_N + t] : s[e].ua;
-            s[e].ya = 0.f; s[e].yd = 0.f; s[e].bad_at = 0; s[e].dself = 0.f;
+            s[e].ya = 0.f; s[e].yd = 0.f; s[e].bad_at = 0; s[e].dself = 0.f; s[e].rkeep = 1.f;
             if (t == 0) sh[e].info = 0;
-            if (m + (i64)gridDim.x * NM < batch) {                            // this slot's next evaluation: its row prefix -> L2
-                const float *nrow = brow + (i64)gridDim.x * NM * (GP_N * GP_N);
-                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nrow), "r"((uint32_t)(128 * (w + 1))) : "memory");
-            }
+            if (STAGED && prefetched) continue;
+            const float cdiag = io.c[m * GP_N + t];
             // ---- load: columns 32c..32c+31 of this row for c <= w (lower triangle), + diag C, into this row's TMEM lane
             float v32[32];
             #pragma unroll
@@ -348,11 +394,17 @@ tc_gp128_kernel(GpIO<float> io, i64 batch, int *__restrict__ info) {
             }
         }
         tmem_st_wait();
+        const i64 m_next = m0 + (i64)gridDim.x * NM;
+        const bool has_next = STAGED && m_next < batch;
+        int staged_chunk = -1;                                                // chunk sitting in the stage, not yet in TMEM
+        const float *__restrict__ nrow = io.b + (has_next ? m_next : m0) * (GP_N * GP_N) + (i64)t * GP_N;
 
         #pragma unroll 1
         for (int p = 0; p < NP; ++p) {
             const int wd = (p * PW) >> 5;                                     // the warp that owns the diagonal block
             const int lane0 = (p * PW) & 31;                                  // its first lane
+            if (STAGED && t == 0 && has_next && ((p + 1) * PW) % 32 == 0)     // bytes the rows will copy after this panel's first barrier
+                mbar_expect_tx(&sh[0].stage_full, (uint32_t)(4 - (((p + 1) * PW) / 32 - 1)) * 32u * 128u);
             if (w >= wd) {
                 if (p > 0) { mbar_wait(mma_done, phase); tc_fence_after(); }  // the updates of panel p-1 have landed
                 #pragma unroll
@@ -369,11 +421,25 @@ tc_gp128_kernel(GpIO<float> io, i64 batch, int *__restrict__ info) {
                 }
                 DiagStep<PW, NM, 0>::run(s, sh, lane, lane0);
                 #pragma unroll
-                for (int e = 0; e < NM; ++e)
+                for (int e = 0; e < NM; ++e) {
+                    if (lane >= lane0 && lane < lane0 + PW) sh[e].rinv[lane - lane0] = s[e].rkeep;
                     if (lane == 0 && s[e].bad_at != 0 && sh[e].info == 0) sh[e].info = p * PW + s[e].bad_at;
+                }
             }
             __syncthreads();
+            // the columns of chunk `pc` are final for every row now: start fetching that chunk of the next evaluation
+            const int pc = (has_next && ((p + 1) * PW) % 32 == 0) ? ((p + 1) * PW) / 32 - 1 : -1;
+            if (STAGED && pc >= 0) {
+                if (pc <= w) bulk_g2s(stage + t * Geo::STAGE_STRIDE, nrow + 32 * pc, 128, &sh[0].stage_full);
+                staged_chunk = pc;
+            }
             if (w > wd) TrsmStep<PW, NM, 0>::run(s, sh);
+            else if (w == wd) {                                               // in the shadow of the other warps' TRSM
+                DiagRhsStep<PW, NM, 0>::run(s, sh, lane, lane0);
+                #pragma unroll
+                for (int e = 0; e < NM; ++e)
+                    if (lane >= lane0 && lane < lane0 + PW) { sh[e].ya[lane - lane0] = s[e].ya; sh[e].yd[lane - lane0] = s[e].yd; }
+            }
             if (w >= wd && p < NP - 1) {                                      // publish the rows' multipliers as hi + lo
                 #pragma unroll
                 for (int e = 0; e < NM; ++e) {
@@ -393,6 +459,10 @@ tc_gp128_kernel(GpIO<float> io, i64 batch, int *__restrict__ info) {
             }
             tc_fence_before();
             __syncthreads();
+            if (w > wd) {                                                     // the block's y are complete: rows below catch up
+                #pragma unroll
+                for (int e = 0; e < NM; ++e) rhs_row_update<PW>(s[e], sh[e]);
+            }
             if (p < NP - 1 && t == 0) {
                 tc_fence_after();
                 const int n_cols = GP_N - PW * (p + 1);
@@ -416,7 +486,50 @@ tc_gp128_kernel(GpIO<float> io, i64 batch, int *__restrict__ info) {
                 }
                 umma_commit(mma_done);
             }
+            if (STAGED && staged_chunk >= 0 && staged_chunk != pc) {          // staged one panel ago: stage -> registers -> TMEM
+                const int c = staged_chunk;
+                if (c <= w) {
+                    mbar_wait(&sh[0].stage_full, stage_phase);
+                    float v32[32];
+                    #pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const float4 v = reinterpret_cast<const float4 *>(stage + t * Geo::STAGE_STRIDE)[q];
+                        v32[4 * q + 0] = v.x; v32[4 * q + 1] = v.y; v32[4 * q + 2] = v.z; v32[4 * q + 3] = v.w;
+                    }
+                    if (c == w) {
+                        const float cnext = io.c[m_next * GP_N + t];
+                        #pragma unroll
+                        for (int j = 0; j < 32; ++j) if (j == lane) v32[j] += cnext;
+                    }
+                    tmem_st32(my_lane + 32 * c, v32);
+                    fence_async_smem();                                       // the stage is rewritten by bulk copies later
+                }
+                stage_phase ^= 1;
+                staged_chunk = -1;
+            }
         }
+        if (STAGED && staged_chunk >= 0) {                                    // the last chunk (rows 96..127 only) of the next evaluation
+            const int c = staged_chunk;
+            if (c <= w) {
+                mbar_wait(&sh[0].stage_full, stage_phase);
+                float v32[32];
+                #pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const float4 v = reinterpret_cast<const float4 *>(stage + t * Geo::STAGE_STRIDE)[q];
+                    v32[4 * q + 0] = v.x; v32[4 * q + 1] = v.y; v32[4 * q + 2] = v.z; v32[4 * q + 3] = v.w;
+                }
+                if (c == w) {
+                    const float cnext = io.c[m_next * GP_N + t];
+                    #pragma unroll
+                    for (int j = 0; j < 32; ++j) if (j == lane) v32[j] += cnext;
+                }
+                tmem_st32(my_lane + 32 * c, v32);
+                fence_async_smem();
+            }
+            stage_phase ^= 1;
+            staged_chunk = -1;
+        }
+        if (STAGED && has_next) prefetched = true;
         // ---- epilogue: means = sum ya*yd, variances = E - sum ya^2 (every row finalised its y in its own panel)
         #pragma unroll
         for (int e = 0; e < NM; ++e) {

@@ -13,6 +13,10 @@ NVFLAGS  := -O3 -std=c++17 $(ARCH) -lineinfo -Xcompiler -fPIC -Xptxas -v $(EXTRA
 ifeq ($(log),1)
 NVFLAGS  += -DDETAILED_LOGGING
 endif
+# `make lab=1`: also build the measured-but-not-default kernel generations (csrc/tile_configs.h, INVGPU_LAB)
+ifeq ($(lab),1)
+NVFLAGS  += -DINVGPU_LAB=1
+endif
 CSRC     := cuda_matrix_inversion_b200/csrc
 LIBDIR   := cuda_matrix_inversion_b200/lib
 LIB      := $(LIBDIR)/libinvgpu.so

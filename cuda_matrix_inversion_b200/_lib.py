@@ -25,6 +25,7 @@ def _load() -> C.CDLL:
     sig = {
         "invgpu_version": (C.c_char_p, []),
         "invgpu_device_count": (_int, []),
+        "invgpu_has_lab": (_int, []),
         "invgpu_set_device": (_int, [_int]),
         "invgpu_error_string": (C.c_char_p, [_int]),
         "invgpu_launch_count": (_i64, []),

@@ -632,7 +632,8 @@ static int spd_stages_ptrs(T *const *As, T *const *Outs, int n, int batch, int s
 // ==========================================================================================
 extern "C" {
 
-const char *invgpu_version(void) { return "invgpu 0.1 (sm_100a)"; }
+const char *invgpu_version(void) { return INVGPU_LAB ? "invgpu 0.2 (sm_100a, +lab)" : "invgpu 0.2 (sm_100a)"; }
+int invgpu_has_lab(void) { return INVGPU_LAB; }
 
 int invgpu_device_count(void) {
     int n = 0;

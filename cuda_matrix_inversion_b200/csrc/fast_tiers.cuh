@@ -175,7 +175,7 @@ static int fast_general(IO io, int n, i64 batch, int *dInfo, cudaStream_t st, De
         which = (e && !strcmp(e, "rowlane")) ? 1 : (e && !strcmp(e, "generic")) ? 2 : (e && !strcmp(e, "colsplit")) ? 3 : (e && !strcmp(e, "tile")) ? 4 : 0;
     }
     if (which == 2) return INVGPU_NO_FAST_PATH;
-    const bool use_roll = which == 0 && n <= (sizeof(T) == 4 ? 64 : 32) && !(n == 8 && std::is_same<IO, StridedIO<T>>::value && dense_aligned_any(io, 8));
+    const bool use_roll = which == 0 && n <= (sizeof(T) == 4 ? 64 : 32);
     if constexpr (std::is_same<IO, StridedIO<T>>::value) {        // dense batches of order exactly 8: one thread per matrix + TMA
         if (which == 0 && n == 8 && dense_aligned(io, 8)) {
 #define INVGPU_GJ8_TRY(TT, NBUF, MINB)                                                               \
@@ -192,7 +192,7 @@ static int fast_general(IO io, int n, i64 batch, int *dInfo, cudaStream_t st, De
             return launch_gj_colsplit<TT, N, CL, WARPS, MINB>(*reinterpret_cast<StridedIO<TT> *>(&io), batch, dInfo, st, ds);
         INVGPU_GJC_ALL(INVGPU_GJC_TRY)
     }
-    if (use_roll) { INVGPU_GJR_ALL(INVGPU_GJR_TRY) }    // rolled lane = row kernel: every n <= 64 that the n = 8 TMA kernel does not take
+    if (use_roll) { INVGPU_GJR_ALL(INVGPU_GJR_TRY) }    // rolled lane = row kernel: every n <= 64 that the n = 8 TMA kernel did not take
     if (((which == 0 || which == 3) && n > INVGPU_GJT_MIN_N(T)) || (which == 4 && n > 16)) { INVGPU_GJT_ALL(INVGPU_GJT_TRY) }
     INVGPU_GJ_ALL(INVGPU_GJ_TRY)
     return INVGPU_NO_FAST_PATH;

@@ -4,6 +4,20 @@
 //   TR x TC = thread grid per matrix, MINB = resident CTAs per SM the register allocator must allow
 #pragma once
 
+// INVGPU_LAB (make lab=1): also build the kernel generations and configurations that were measured and NOT made the
+// default -- the three-sweep tile inverse, the unrolled one-sweep kernels above n = 8, sweep variants 1 / 3 / 4 (other thread
+// grids, 2x2 block pivots), TMA variants 6 / 7, the unrolled lane = row and the column-split Gauss-Jordan kernels.  They stay
+// selectable through the INVGPU_* environment knobs of INTEGRATION.md and keep their parity tests (skipped without the flag);
+// a default build ships only what the dispatcher can reach.
+#ifndef INVGPU_LAB
+#define INVGPU_LAB 0
+#endif
+#if INVGPU_LAB
+#define INVGPU_LAB_ONLY(...) __VA_ARGS__
+#else
+#define INVGPU_LAB_ONLY(...)
+#endif
+
 #ifndef INVGPU_F32_N32_MINB
 #define INVGPU_F32_N32_MINB 2
 #endif
@@ -13,23 +27,23 @@
 #endif
 
 // fp32 SPD inverse, warp tiers
-#define INVGPU_TILE_SPD_F32_INV(X)                              \
+#define INVGPU_TILE_SPD_F32_INV(X) INVGPU_LAB_ONLY(             \
     X(float, 8, 1, 1, true, 7, 4)                               \
     X(float, 16, 2, 2, true, 7, 4)                              \
     X(float, 32, INVGPU_F32_N32_TR, INVGPU_F32_N32_TC, true, 7, INVGPU_F32_N32_MINB)            \
-    X(float, 64, 8, 4, true, 7, 3)
+    X(float, 64, 8, 4, true, 7, 3))
 // fp32 SPD inverse, CTA tier
-#define INVGPU_TILE_SPD_F32_INV_CTA(X)                          \
-    X(float, 128, 16, 16, true, 7, 2)
+#define INVGPU_TILE_SPD_F32_INV_CTA(X) INVGPU_LAB_ONLY(         \
+    X(float, 128, 16, 16, true, 7, 2))
 
 // fp64 SPD inverse
-#define INVGPU_TILE_SPD_F64_INV(X)                              \
+#define INVGPU_TILE_SPD_F64_INV(X) INVGPU_LAB_ONLY(             \
     X(double, 8, 1, 1, true, 7, 2)                              \
     X(double, 16, 2, 2, true, 7, 2)                             \
     X(double, 32, 4, 4, true, 7, 2)                             \
-    X(double, 64, 8, 8, true, 7, 4)
-#define INVGPU_TILE_SPD_F64_INV_CTA(X)                          \
-    X(double, 128, 16, 16, true, 7, 1)
+    X(double, 64, 8, 8, true, 7, 4))
+#define INVGPU_TILE_SPD_F64_INV_CTA(X) INVGPU_LAB_ONLY(         \
+    X(double, 128, 16, 16, true, 7, 1))
 
 // fused GP mean / variance
 #define INVGPU_TILE_GP_F32(X)                                   \
@@ -68,14 +82,14 @@
 #endif
 // n = 64 fp32: two rows per lane, one warp per matrix, 250 registers: 0.108 vs 0.068 for the 8 x 4 tile kernel (n = 48: 0.054 vs 0.045)
 #define INVGPU_GJ64_F32(X) X(float, 64, 2, 2)
-#define INVGPU_GJ_F32(X) X(float, 8, 1, 4) X(float, 16, INVGPU_GJ16_ROWS, INVGPU_GJ16_MINB) X(float, 32, INVGPU_GJ32_ROWS, INVGPU_GJ32_MINB) INVGPU_GJ64_F32(X)
+#define INVGPU_GJ_F32(X) INVGPU_LAB_ONLY(X(float, 8, 1, 4) X(float, 16, INVGPU_GJ16_ROWS, INVGPU_GJ16_MINB) X(float, 32, INVGPU_GJ32_ROWS, INVGPU_GJ32_MINB) INVGPU_GJ64_F32(X))
 #ifndef INVGPU_GJ16_ROWS_F64
 #define INVGPU_GJ16_ROWS_F64 2
 #endif
 #ifndef INVGPU_GJ32_MINB_F64
 #define INVGPU_GJ32_MINB_F64 4
 #endif
-#define INVGPU_GJ_F64(X) X(double, 8, 1, 4) X(double, 16, INVGPU_GJ16_ROWS_F64, 4) X(double, 32, 1, INVGPU_GJ32_MINB_F64)
+#define INVGPU_GJ_F64(X) INVGPU_LAB_ONLY(X(double, 8, 1, 4) X(double, 16, INVGPU_GJ16_ROWS_F64, 4) X(double, 32, 1, INVGPU_GJ32_MINB_F64))
 #define INVGPU_GJ_ALL(X) INVGPU_GJ_F32(X) INVGPU_GJ_F64(X)
 
 // lane = row Gauss-Jordan with the ROLLED pivot loop (gj_roll_kernels.cuh: rotating register window, deferred row
@@ -106,8 +120,8 @@
 #endif
 // (n = 64 stays on the three-sweep kernel: without compile-time pruning of the shrinking trailing
 //  matrix the one-sweep form does more FMAs, and at n = 64 the kernel is no longer latency-bound)
-#define INVGPU_ONESWEEP_F32(X) X(float, 8, 1, 1, true, 4) X(float, 16, 2, 2, false, 4) X(float, 32, INVGPU_OS_F32_N32_TR, INVGPU_OS_F32_N32_TC, false, INVGPU_OS_F32_N32_MINB)
-#define INVGPU_ONESWEEP_F64(X) X(double, 8, 1, 1, true, 2) X(double, 16, 2, 2, false, 2) X(double, 32, 4, 4, false, 2)
+#define INVGPU_ONESWEEP_F32(X) X(float, 8, 1, 1, true, 4) INVGPU_LAB_ONLY(X(float, 16, 2, 2, false, 4) X(float, 32, INVGPU_OS_F32_N32_TR, INVGPU_OS_F32_N32_TC, false, INVGPU_OS_F32_N32_MINB))
+#define INVGPU_ONESWEEP_F64(X) X(double, 8, 1, 1, true, 2) INVGPU_LAB_ONLY(X(double, 16, 2, 2, false, 2) X(double, 32, 4, 4, false, 2))
 #define INVGPU_ONESWEEP_ALL(X) INVGPU_ONESWEEP_F32(X) INVGPU_ONESWEEP_F64(X)
 
 // SPD inverse, look-ahead sweep kernel (sweep_kernels.cuh):  X(V, T, N, TR, TC, UNROLL, MINB, BLK)
@@ -115,12 +129,12 @@
 // INVGPU_SWEEP_VARIANT=V (tools/kbench.py experiments).  BLK = 1: scalar pivots, 2: 2x2 block pivots.
 #define INVGPU_SWEEP_F32(X)                                                                     \
     X(0, float, 16, 2, 2, false, 4, 1)                                                          \
-    X(0, float, 32, 2, 4, false, 3, 1) X(1, float, 32, 4, 2, false, 3, 1) X(4, float, 32, 2, 4, false, 3, 2) \
-    X(0, float, 64, 4, 4, false, 2, 1) X(3, float, 64, 8, 4, false, 3, 1) X(4, float, 64, 4, 4, false, 2, 2) \
-    X(0, float, 128, 8, 8, false, 2, 1) X(3, float, 128, 16, 8, false, 3, 1) X(4, float, 128, 8, 8, false, 2, 2)
+    X(0, float, 32, 2, 4, false, 3, 1) INVGPU_LAB_ONLY(X(1, float, 32, 4, 2, false, 3, 1) X(4, float, 32, 2, 4, false, 3, 2)) \
+    X(0, float, 64, 4, 4, false, 2, 1) INVGPU_LAB_ONLY(X(3, float, 64, 8, 4, false, 3, 1) X(4, float, 64, 4, 4, false, 2, 2)) \
+    X(0, float, 128, 8, 8, false, 2, 1) INVGPU_LAB_ONLY(X(3, float, 128, 16, 8, false, 3, 1) X(4, float, 128, 8, 8, false, 2, 2))
 #define INVGPU_SWEEP_F64(X)                                                                     \
     X(0, double, 16, 2, 2, false, 2, 1) X(0, double, 32, 4, 4, false, 2, 1) X(0, double, 64, 8, 8, false, 4, 1) X(0, double, 128, 16, 16, false, 1, 1) \
-    X(4, double, 64, 8, 8, false, 4, 2) X(4, double, 128, 16, 16, false, 1, 2)
+    INVGPU_LAB_ONLY(X(4, double, 64, 8, 8, false, 4, 2) X(4, double, 128, 16, 16, false, 1, 2))
 // Measured on B200, fraction of the HBM roofline (tools/kbench.py, gpurun_out/o_kbench.log), BLK = 1 vs BLK = 2:
 //   fp32 n = 32: 0.51 vs 0.44   64: 0.28 vs 0.25   128: 0.18 vs 0.165   fp64 64: 0.229 vs 0.232   128: 0.112 vs 0.116
 // BLK = 0 (no look-ahead: publish -> barrier -> update through one rolled body per range, half the code):
@@ -145,7 +159,7 @@
 #ifndef INVGPU_TMA_N32_MINB
 #define INVGPU_TMA_N32_MINB 3
 #endif
-#define INVGPU_SWEEP_TMA_F32(X) X(0, float, 32, 2, 4, false, INVGPU_TMA_N32_MINB, false, true) X(6, float, 32, 2, 4, false, 3, false, false) X(7, float, 32, 2, 4, false, 3, true, false)
+#define INVGPU_SWEEP_TMA_F32(X) X(0, float, 32, 2, 4, false, INVGPU_TMA_N32_MINB, false, true) INVGPU_LAB_ONLY(X(6, float, 32, 2, 4, false, 3, false, false) X(7, float, 32, 2, 4, false, 3, true, false))
 // fp64 with interleaved lanes and per-lane bulk-copy tile I/O (padded slots instead of swizzle; tried, not kept):
 // n = 32: 0.382 vs 0.418 direct, n = 16: 0.553 vs 0.574 -- at half-rate DFMA and 192-204 registers it does not pay.
 #define INVGPU_SWEEP_TMA_F64(X)
@@ -157,7 +171,7 @@
 // Only the CTA tier gains (one barrier per pivot instead of the rolled potrf's per-pivot chain), so only
 // that one is dispatched (8 x 8 threads with 16 x 16 tiles: 0.183, with 2x2 block pivots 0.177; 16 x 8 threads with 2x2 block
 // pivots: 0.123; 8 x 16 scalar pivots: 0.118; the sweep on 4 x 4 lanes at n = 64: 0.325 vs 0.386 for the tile kernel); the warp tiers stay on the fully unrolled tile kernels with exact static pruning.
-#define INVGPU_SWEEP_GP_F32(X) X(0, float, 128, 8, 8, false, 2, 1) X(3, float, 128, 16, 8, false, 3, 2)
+#define INVGPU_SWEEP_GP_F32(X) X(0, float, 128, 8, 8, false, 2, 1) INVGPU_LAB_ONLY(X(3, float, 128, 16, 8, false, 3, 2))
 #define INVGPU_SWEEP_GP_F64(X)
 #define INVGPU_SWEEP_GP_ALL(X) INVGPU_SWEEP_GP_F32(X) INVGPU_SWEEP_GP_F64(X)
 
@@ -208,7 +222,7 @@
 #define INVGPU_GP_THREAD_ALL(X) INVGPU_GP_THREAD_F32(X) INVGPU_GP_THREAD_F64(X)
 
 // general inverse, column-split lanes, matrix in registers (gj_colsplit_kernel):  X(T, N, CL, WARPS, MINB)
-#define INVGPU_GJC_F32(X) X(float, 16, 8, 4, 2) X(float, 32, 4, 4, 2)
-#define INVGPU_GJC_F64(X) X(double, 16, 4, 4, 2)
+#define INVGPU_GJC_F32(X) INVGPU_LAB_ONLY(X(float, 16, 8, 4, 2) X(float, 32, 4, 4, 2))
+#define INVGPU_GJC_F64(X) INVGPU_LAB_ONLY(X(double, 16, 4, 4, 2))
 #define INVGPU_GJC_ALL(X) INVGPU_GJC_F32(X) INVGPU_GJC_F64(X)
 #define INVGPU_GJC_DEFAULT(TT) false                  // INVGPU_GJ_KERNEL=colsplit only: fp32 0.227 / 0.122 vs 0.289 / 0.203 for the lean lane = row kernel, fp64 n = 16 0.245 vs 0.311

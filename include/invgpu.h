@@ -40,6 +40,9 @@ typedef long long invgpu_i64;
 
 /* ---- library / device ------------------------------------------------------------------ */
 const char *invgpu_version(void);
+/* 1 when the library was built with `make lab=1`: the measured-but-not-default kernel generations behind the INVGPU_*
+ * environment knobs are present (see csrc/tile_configs.h); 0 in a default build, where those knobs fall back to the defaults. */
+int invgpu_has_lab(void);
 int invgpu_device_count(void);                 /* 0 when no CUDA device is usable */
 int invgpu_set_device(int device);             /* cudaSetDevice for the calling host thread (multi-GPU sharding) */
 const char *invgpu_error_string(int code);

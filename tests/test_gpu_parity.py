@@ -743,6 +743,9 @@ def test_sweep_kernel_variants(variant, n):
     per process with INVGPU_SWEEP_VARIANT, so each runs in a child process: oracle parity, flags, ragged tail."""
     import subprocess
     import sys
+    from cuda_matrix_inversion_b200 import lib
+    if variant not in (0, 9) and not lib.invgpu_has_lab():
+        pytest.skip("non-default kernel configuration: built only with `make lab=1`")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     env = dict(os.environ, INVGPU_SWEEP_VARIANT=str(variant), INVGPU_TRACE="1")
     batch = 1027 if n <= 32 else 131
@@ -790,6 +793,9 @@ def test_general_kernel_variants(kernel, n, dtype):
     one child process each, oracle parity, sgetrf flags (zero column, zero matrix, NaN column), ragged tail."""
     import subprocess
     import sys
+    from cuda_matrix_inversion_b200 import lib
+    if kernel in ("colsplit", "rowlane") and not lib.invgpu_has_lab():
+        pytest.skip("non-default kernel generation: built only with `make lab=1`")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     env = dict(os.environ, INVGPU_GJ_KERNEL=kernel)
     tol = 1e-4 if dtype == "float32" else 1e-10

@@ -18,7 +18,12 @@
 // so lane r writes its values to row pi^-1(r) = "the step at which I was the pivot", column pi(c):
 // for a fixed c the lanes of a matrix write one contiguous, fully used line -- coalesced without any
 // staging.  Loads are coalesced the same way (column-major input, consecutive rows in consecutive
-// lanes).  Arithmetic per element is exactly the oracle's (scale the pivot row, then a -= f * row).
+// lanes).  Arithmetic: the ROWS > 2 form scales the pivot row and subtracts like the oracle; the lean form (ROWS <= 2,
+// fp32) uses rcp.approx.f32 and the multiplier form z = -a * r with two in-place FMAs per element, which differs from
+// the oracle in rounding only (bounded against the fp64 truth by tests/util.py::assert_general_parity and the
+// ill-conditioned test in tests/test_dropin_gpu.py).  Non-finite INPUTS give undefined output: the select-free second
+// FMA (a += 0 * row) turns an Inf / NaN of a pivot row into NaN in every row, without touching info.
+// Since round 2 this kernel is built only by `make lab=1`; gj_roll_kernels.cuh is the default for these sizes.
 //
 // Runtime order n <= N: the matrix is embedded as blockdiag(A, I); padded rows can only win padded
 // columns, so pivots, flags and results of A are unaffected.

@@ -61,6 +61,13 @@ template <> __device__ __forceinline__ void load_two_pairs<float>(const float *p
     const float4 v = *reinterpret_cast<const float4 *>(p);
     r0.x = v.x; r0.y = v.y; r1.x = v.z; r1.y = v.w;
 }
+// publish one register pair of the pivot row: 64-bit stores straight from the FFMA2 register pairs (a merged 128-bit store
+// costs four staging moves per store: the first version of this kernel spent 19 % of its issue slots on them; a variant with
+// four pivots per iteration and quad-aligned 128-bit publish stores still needed the moves and measured 7 % slower)
+template <typename T> __device__ __forceinline__ void store_pair(T *p, GjPair<T> v) { *reinterpret_cast<GjPair<T> *>(p) = v; }
+template <> __device__ __forceinline__ void store_pair<float>(float *p, GjPair<float> v) {
+    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"((unsigned)__cvta_generic_to_shared(p)), "f"(v.x), "f"(v.y) : "memory");
+}
 template <typename T> __device__ __forceinline__ T fast_rcp(T x) { return T(1) / x; }
 template <> __device__ __forceinline__ float fast_rcp<float>(float x) { float r; asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
@@ -194,7 +201,7 @@ gj_roll_kernel(IO io, int n_runtime, i64 batch, int *__restrict__ info) {
                     ca[q] = isp ? T(1) : z[q];
                     if (isp) {                                     // one branch per row slot: static register names
                         #pragma unroll
-                        for (int i = 0; i < H; ++i) *reinterpret_cast<GjPair<T> *>(pr + 2 * i) = ap[q][i];
+                        for (int i = 0; i < H; ++i) store_pair<T>(pr + 2 * i, ap[q][i]);
                         piv[2 * kk] = l + L * q;
                         pivoted[q] = true; mystep[q] = 2 * kk; rscale[q] = r;
                     }
@@ -232,7 +239,7 @@ gj_roll_kernel(IO io, int n_runtime, i64 batch, int *__restrict__ info) {
                     cb[q] = isp ? T(1) : z[q];
                     if (isp) {
                         #pragma unroll
-                        for (int i = 1; i < H; ++i) *reinterpret_cast<GjPair<T> *>(pr + 2 * i) = ap[q][i];
+                        for (int i = 1; i < H; ++i) store_pair<T>(pr + 2 * i, ap[q][i]);
                         pr[N] = ca[q];                             // the pending column of the pivot row
                         piv[2 * kk + 1] = l + L * q;
                         pivoted[q] = true; mystep[q] = 2 * kk + 1; rscale[q] = r;

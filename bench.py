@@ -67,9 +67,9 @@ GP_UNIT = "evaluations/s"
 # BASELINE configs[4]: mixed dimensions, 4 M matrices on 8 GPUs = 500 000 per GPU (weak scaling)
 MIXED_PER_GPU = 500_000
 # dram__bytes_read.sum + dram__bytes_write.sum of the headline kernel from the committed `ncu --set full` capture
-# (2^18 matrices per launch there: 1.075257 GB read + 1.026820 GB written), scaled to the 2^20 of one bench launch
-NCU_DRAM_BYTES_PER_LAUNCH = int((1.075257e9 + 1.026820e9) * 4)
-NCU_TRAFFIC_SOURCE = "profiles/r1_sweep32_tma_interleaved_summary.md (ncu --set full, 2^18 matrices) x 4"
+# (2^18 matrices per launch there: 1.075248 GB read + 1.027806 GB written), scaled to the 2^20 of one bench launch
+NCU_DRAM_BYTES_PER_LAUNCH = int((1.075248e9 + 1.027806e9) * 4)
+NCU_TRAFFIC_SOURCE = "profiles/r2_sweep32_tma_interleaved_summary.md (ncu --set full, 2^18 matrices) x 4"
 
 
 def _peaks():

@@ -336,11 +336,17 @@ static int host_pipeline(std::vector<HostArr> &arrs, i64 batch, int *info, int *
     const bool logging = detailed_logging();
     std::vector<cudaEvent_t> tev;                    // six timing events per chunk when logging
     auto stamp = [&](cudaStream_t st) { if (logging) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); tev.push_back(e); } };
-    auto drain = [&](i64 c) -> int {
+    // Staging copy of a finished chunk's outputs (pageable user buffers only).  Inside the chunk loop it runs on a helper
+    // thread BESIDE the staging copy of the next chunk's inputs (they touch different regions of the ring slot); it is joined
+    // before the slot's next device-to-host copy is queued.
+    std::thread out_thr;
+    auto join_out = [&]() { if (out_thr.joinable()) out_thr.join(); };
+    auto drain = [&](i64 c, bool async) -> int {
         const int slot = (int)(c % S);
         INVGPU_TRY(cudaEventSynchronize(ds->ev_out[slot]));
         const i64 first = c * cu;
         const i64 cnt = (first + cu <= batch) ? cu : batch - first;
+        bool copies = false;
         for (auto &a : arrs) {
             if (a.in) continue;
             const bool is_info = (&a == &arrs.back());
@@ -352,14 +358,24 @@ static int host_pipeline(std::vector<HostArr> &arrs, i64 batch, int *info, int *
                     if (info) info[first + i] = ci[i];
                 }
             } else if (!a.pinned && a.out) {
-                staging_copy(a.out + (size_t)first * a.unit, ring, (size_t)cnt * a.unit);
+                copies = true;
             }
         }
+        if (!copies) return 0;
+        auto copy_all = [&arrs, ds, slot, first, cnt]() {
+            for (auto &a : arrs) {
+                if (a.in || &a == &arrs.back() || a.pinned || !a.out) continue;
+                staging_copy(a.out + (size_t)first * a.unit, (const char *)ds->h_ring[slot] + a.off, (size_t)cnt * a.unit);
+            }
+        };
+        join_out();
+        if (async) out_thr = std::thread(copy_all); else copy_all();
         return 0;
     };
     // an error in the middle of the stream of chunks: nothing may still be reading the caller's buffers or the
     // ring when we return, so wait for everything that has been queued
     auto fail = [&](int code) -> int {
+        join_out();
         cudaStreamSynchronize(ds->s_in); cudaStreamSynchronize(ds->s_comp); cudaStreamSynchronize(ds->s_out);
         cudaGetLastError();
         return code;
@@ -368,7 +384,7 @@ static int host_pipeline(std::vector<HostArr> &arrs, i64 batch, int *info, int *
 
     for (i64 c = 0; c < nchunks; ++c) {
         const int slot = (int)(c % S);
-        if (c >= S) { rc = drain(c - S); if (rc) return fail(rc); }
+        if (c >= S) { rc = drain(c - S, true); if (rc) return fail(rc); }
         const i64 first = c * cu;
         const i64 cnt = (first + cu <= batch) ? cu : batch - first;
         char *dbase = (char *)ds->d_ws[slot];
@@ -392,6 +408,7 @@ static int host_pipeline(std::vector<HostArr> &arrs, i64 batch, int *info, int *
         stamp(ds->s_comp);
         INVGPU_PIPE_TRY(cudaEventRecord(ds->ev_comp[slot], ds->s_comp));
         INVGPU_PIPE_TRY(cudaStreamWaitEvent(ds->s_out, ds->ev_comp[slot], 0));
+        join_out();                                              // the slot's previous outputs have left the ring
         stamp(ds->s_out);
         for (auto &a : arrs) {
             if (a.in || (!a.out && &a != &arrs.back())) continue;
@@ -402,7 +419,8 @@ static int host_pipeline(std::vector<HostArr> &arrs, i64 batch, int *info, int *
         stamp(ds->s_out);
         INVGPU_PIPE_TRY(cudaEventRecord(ds->ev_out[slot], ds->s_out));
     }
-    for (i64 c = (nchunks > S ? nchunks - S : 0); c < nchunks; ++c) { rc = drain(c); if (rc) return fail(rc); }
+    for (i64 c = (nchunks > S ? nchunks - S : 0); c < nchunks; ++c) { rc = drain(c, false); if (rc) return fail(rc); }
+    join_out();
 #undef INVGPU_PIPE_TRY
     if (logging) {
         g_phases = PhaseTimes();
@@ -536,7 +554,17 @@ static int run_mixed_spd(T *const *hIn, T *const *hOut, const int *hN, i64 count
     // work list + tickets of THIS call: the next buffer of a small ring; it is free again when the event recorded
     // behind the last tier kernel of the call that used it before has completed (calls on other streams or from
     // other host threads therefore never overwrite a list that kernels still read)
-    DeviceState::MixedBuf &mb = ds->mixed[ds->mixed_next++ % DeviceState::kMixedRing];
+    // prefer a buffer that is free already and large enough (no allocation, no wait); then any free one; only when all are
+    // in flight wait for the oldest.  (Plain round robin made the first kMixedRing calls allocate pinned memory each: with
+    // eight ranks pinning at once that cost tens of milliseconds per call on the 8-GPU box.)
+    int pick = -1;
+    for (int i = 0; i < DeviceState::kMixedRing && pick < 0; ++i)
+        if (ds->mixed[i].bytes >= need && cudaEventQuery(ds->mixed[i].done) == cudaSuccess) pick = i;
+    for (int i = 0; i < DeviceState::kMixedRing && pick < 0; ++i)
+        if (cudaEventQuery(ds->mixed[i].done) == cudaSuccess) pick = i;
+    cudaGetLastError();                                       // cudaErrorNotReady of the queries is not an error
+    if (pick < 0) pick = (int)(ds->mixed_next++ % DeviceState::kMixedRing);
+    DeviceState::MixedBuf &mb = ds->mixed[pick];
     INVGPU_TRY(cudaEventSynchronize(mb.done));
     if (mb.bytes < need) {
         if (mb.d) cudaFree(mb.d);

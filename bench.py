@@ -64,6 +64,10 @@ GP_N = 128
 GP_BATCH = 200_000
 GP_METRIC = "fused GP-mean evaluations/sec (128x128 fp32)"
 GP_UNIT = "evaluations/s"
+# dram__bytes_read.sum + dram__bytes_write.sum of the tcgen05 GP kernel per evaluation, from the committed `ncu --set full` capture
+# (9 472 evaluations: 405.01 MB read -- only the upper triangle of B is fetched -- + 4.47 MB written)
+GP_NCU_DRAM_BYTES_PER_EVAL = (405.006592e6 + 4.473856e6) / 9472
+GP_NCU_TRAFFIC_SOURCE = "profiles/r2_tc_gp128_summary.md (ncu --set full, 9472 evaluations), scaled to the evaluations of one launch"
 # BASELINE configs[4]: mixed dimensions, 4 M matrices on 8 GPUs = 500 000 per GPU (weak scaling)
 MIXED_PER_GPU = 500_000
 # dram__bytes_read.sum + dram__bytes_write.sum of the headline kernel from the committed `ncu --set full` capture
@@ -457,6 +461,21 @@ def run_ours(args):
 
     ceil_s = timed_host(ceil_step, e2e_steps, 1)
     ceil_value = world * BATCH * e2e_steps / ceil_s
+    # the same two calls with rank 0 ALONE on the box (the other ranks wait at the barrier): what one GPU gets when nobody else
+    # uses the host path -- end-to-end weak-scaling efficiency = e2e / (N x this), and the same for the copy-only ceiling
+    e2e_single = ceil_single = None
+    if world > 1:
+        barrier()
+        if rank == 0:
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                e2e_step()
+            e2e_single = BATCH * e2e_steps / (time.perf_counter() - t0)
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                ceil_step()
+            ceil_single = BATCH * e2e_steps / (time.perf_counter() - t0)
+        barrier()
     h_in.free(); h_out.free()
 
     # final gather: one checksum scalar per rank (the only inter-GPU exchange of this workload)
@@ -584,7 +603,12 @@ def run_ours(args):
                     "per_gpu": e2e_value / world, "host_GBps_aggregate": world * (h2d + d2h) * e2e_steps / e2e_s / 1e9,
                     "ceiling": ceil_value, "frac_of_ceiling": e2e_value / ceil_value,
                     "ceiling_what": "invgpu_xfer_roundtrip_host: the same host pipeline with the kernel replaced by a device copy, "
-                                    "same bytes, all ranks concurrently"},
+                                    "same bytes, all ranks concurrently",
+                    "single_gpu_value": e2e_single, "single_gpu_ceiling": ceil_single,
+                    "weak_scaling_efficiency": (e2e_value / (world * e2e_single)) if e2e_single else None,
+                    "ceiling_weak_scaling_efficiency": (ceil_value / (world * ceil_single)) if ceil_single else None,
+                    "efficiency_what": "e2e (resp. copy-only ceiling) at N ranks / (N x the same call with rank 0 alone on this box): "
+                                       "how far the box's shared host<->device path lets N GPUs scale"},
             "e2e_ceiling": ceil_value,
             "gp_mean_128": {
                 "metric": GP_METRIC, "value": gp_value, "unit": GP_UNIT, "scaling": "strong", "batch_total": GP_BATCH,
@@ -593,7 +617,8 @@ def run_ours(args):
                                        f"contiguous shards over {world} GPU(s), final all_gather of the scalars",
                            "kernel_tier": api.tier_name("gp", n)},
                 "roofline": {"bound": "hbm", "achieved": gp_ach, "peak": hbm_peak, "unit": "GB/s", "frac": gp_ach / hbm_peak,
-                             "algorithmic_bytes_per_launch": gp_algo, "kernel_ms": gp_kernel_ms, "traffic": None,
+                             "algorithmic_bytes_per_launch": gp_algo, "kernel_ms": gp_kernel_ms,
+                             "traffic": int(GP_NCU_DRAM_BYTES_PER_EVAL * gb), "traffic_source": GP_NCU_TRAFFIC_SOURCE,
                              "fp32_flops_per_eval": n ** 3 / 3 + 2 * n * n + 3 * n},
                 "gather_ms": gather_ms, "checksum": gp_checksum, "gpu_launches": gp_launches,
                 "e2e": {"value": gp_e2e_value, "unit": GP_UNIT, "h2d_bytes_per_step": gb * (n * n + 3 * n) * 4,

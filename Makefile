@@ -31,6 +31,7 @@ CUOBJS   := $(LIBDIR)/capi.o $(patsubst $(CSRC)/%.cu,$(LIBDIR)/%.o,$(wildcard $(
 $(LIBDIR)/%.o: $(CSRC)/%.cu $(HDRS)
 	@mkdir -p $(LIBDIR)
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(LIBDIR)/ptxas_$*.log || (cat $(LIBDIR)/ptxas_$*.log; false)
+	@sed -i '/Compile time/d' $(LIBDIR)/ptxas_$*.log
 
 $(LIBDIR)/mats_io.o: $(CSRC)/mats_io.c include/helper_cpu.h include/types.h
 	@mkdir -p $(LIBDIR)

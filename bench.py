@@ -17,7 +17,9 @@ One JSON line on stdout (rank 0):
             inverse_cholesky_batched_gpu without the abort), pinned HOST buffers in, HOST buffers
             out, H2D + D2H inside the timed region; `ceiling` / `e2e_ceiling` = the same pipeline with the
             kernel replaced by a device copy (copy-only: what the box's host<->device path allows with all
-            ranks transferring at once), `frac_of_ceiling` = e2e / ceiling
+            ranks transferring at once), `frac_of_ceiling` = e2e / ceiling; at N > 1 also `single_gpu_value` /
+            `single_gpu_ceiling` (rank 0 alone on the same box, the other ranks idle at a barrier) and
+            `weak_scaling_efficiency` / `ceiling_weak_scaling_efficiency` = N-rank number / (N x the single one)
   roofline  algorithmic bytes (2 n^2 sizeof(T) per matrix) / measured kernel time vs the measured
             HBM copy peak in MEASURED_PEAKS.json
   cpu_baseline  the reference's own CPU path (oracle/_ref: inverse_chol_blas_omp, src/inverse.c:100,

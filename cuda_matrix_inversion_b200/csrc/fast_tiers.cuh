@@ -161,6 +161,11 @@ template <typename T, typename TT> struct IOCast<PtrIO<T>, TT> { typedef PtrIO<T
         return launch_gj_roll<TT, N, ROWS, typename IOCast<IO, TT>::type, MINB>(                     \
             *reinterpret_cast<typename IOCast<IO, TT>::type *>(&io), n, batch, dInfo, st, ds);
 
+#define INVGPU_GJR2_TRY(TT, N, CW, MINB)                                                            \
+    if (std::is_same<T, TT>::value && n <= N)                                                        \
+        return launch_gj_roll2d<TT, N, CW, typename IOCast<IO, TT>::type, MINB>(                         \
+            *reinterpret_cast<typename IOCast<IO, TT>::type *>(&io), n, batch, dInfo, st, ds);
+
 // 2-D tile Gauss-Jordan: smallest instantiated padded order >= n wins (ascending lists)
 #define INVGPU_GJT_TRY(TT, N, TR, TC, MINB)                                                         \
     if (std::is_same<T, TT>::value && n <= N)                                                        \
@@ -193,6 +198,7 @@ static int fast_general(IO io, int n, i64 batch, int *dInfo, cudaStream_t st, De
         INVGPU_GJC_ALL(INVGPU_GJC_TRY)
     }
     if (use_roll) { INVGPU_GJR_ALL(INVGPU_GJR_TRY) }    // rolled lane = row kernel: every n <= 64 that the n = 8 TMA kernel did not take
+    if (which == 0 && sizeof(T) == 4 && n > 64) { INVGPU_GJR2_ALL(INVGPU_GJR2_TRY) }   // one CTA per matrix, rolled (fp32 65 .. 128)
     if (((which == 0 || which == 3) && n > INVGPU_GJT_MIN_N(T)) || (which == 4 && n > 16)) { INVGPU_GJT_ALL(INVGPU_GJT_TRY) }
     INVGPU_GJ_ALL(INVGPU_GJ_TRY)
     return INVGPU_NO_FAST_PATH;
@@ -252,6 +258,8 @@ static int fast_padded(PadIO<T> io, int tier_n, i64 batch, int *dInfo, cudaStrea
     if (op == 1 && n <= N && dtype_bytes == (int)sizeof(TT)) return "warp-rowlane";
 #define INVGPU_GJR_NAME(TT, N, ROWS, MINB) \
     if (op == 1 && n <= N && dtype_bytes == (int)sizeof(TT)) return "warp-rowlane-rolled";
+#define INVGPU_GJR2_NAME(TT, N, CW, MINB) \
+    if (op == 1 && n > 64 && n <= N && dtype_bytes == (int)sizeof(TT)) return "cta-roll2d";
 #define INVGPU_THREAD_BULK_NAME(TT, N, WARPS, MINB) \
     if (op == 0 && n == N && dtype_bytes == (int)sizeof(TT)) return "thread-bulk";
 #define INVGPU_SPD8_NAME(TT, NBUF, MINB) \
@@ -272,6 +280,7 @@ static const char *fast_tier_name(int op, int n, int dtype_bytes) {
     INVGPU_SPD8_TMA_ALL(INVGPU_GJ8_NAME)
     INVGPU_GJC_ALL(INVGPU_GJC_NAME)
     INVGPU_GJR_ALL(INVGPU_GJR_NAME)
+    INVGPU_GJR2_ALL(INVGPU_GJR2_NAME)
     INVGPU_GJT_ALL(INVGPU_GJT_NAME)
     INVGPU_GJ_ALL(INVGPU_GJ_NAME)
     INVGPU_TILE_SPD_ALL(INVGPU_TILE_NAME)

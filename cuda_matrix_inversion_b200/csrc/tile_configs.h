@@ -110,6 +110,16 @@
 #define INVGPU_GJR_F64(X) X(double, 8, 1, 4) X(double, 16, 2, 4) X(double, 32, 1, 4)
 #define INVGPU_GJR_ALL(X) INVGPU_GJR_F32(X) INVGPU_GJR_F64(X)
 
+// one CTA per matrix, 32 lanes x N / CW warps, rolled pivot loop (gj_roll2d_kernels.cuh), fp32 64 < n <= 128:  X(T, N, CW, MINB)
+#ifndef INVGPU_GJR2_CW
+#define INVGPU_GJR2_CW 32
+#endif
+#ifndef INVGPU_GJR2_MINB
+#define INVGPU_GJR2_MINB 3
+#endif
+#define INVGPU_GJR2_F32(X) X(float, 128, INVGPU_GJR2_CW, INVGPU_GJR2_MINB)
+#define INVGPU_GJR2_ALL(X) INVGPU_GJR2_F32(X)
+
 // SPD inverse, one-sweep Cholesky (onesweep_kernels.cuh), warp tiers:  X(T, N, TR, TC, STAGE, MINB)
 #ifndef INVGPU_OS_F32_N32_MINB
 #define INVGPU_OS_F32_N32_MINB 5

@@ -22,6 +22,9 @@ int launch_gj_tile(IO io, int n, i64 batch, int *dInfo, cudaStream_t st, DeviceS
 template <typename T, int N, int ROWS, typename IO, int MINB>
 int launch_gj_roll(IO io, int n, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds);
 
+template <typename T, int N, int CW, typename IO, int MINB>
+int launch_gj_roll2d(IO io, int n, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds);
+
 template <typename T, int N, int CL, int WARPS, int MINB>
 int launch_gj_colsplit(StridedIO<T> io, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds);
 
@@ -65,6 +68,7 @@ int launch_tc_gp128(GpIO<float> io, i64 batch, int *dInfo, cudaStream_t st, Devi
 #include "tile_kernels.cuh"
 #include "gj_kernels.cuh"
 #include "gj_roll_kernels.cuh"
+#include "gj_roll2d_kernels.cuh"
 #include "onesweep_kernels.cuh"
 #include "sweep_kernels.cuh"
 #include "gj_tile_kernels.cuh"
@@ -283,6 +287,19 @@ int launch_gj_roll(IO io, int n, i64 batch, int *dInfo, cudaStream_t st, DeviceS
     return (int)cudaGetLastError();
 }
 
+template <typename T, int N, int CW, typename IO, int MINB>
+int launch_gj_roll2d(IO io, int n, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds) {
+    using G = GjRoll2dGeo<T, N, CW>;
+    auto kern = (n == N) ? gj_roll2d_kernel<T, N, CW, IO, MINB, true> : gj_roll2d_kernel<T, N, CW, IO, MINB, false>;
+    const size_t smem = (size_t)G::WORDS * sizeof(T);
+    int grid = 0;
+    int rc = persistent_grid(kern, G::BLOCK, smem, batch, ds, &grid);
+    if (rc) return rc;
+    kern<<<grid, G::BLOCK, smem, st>>>(io, n, batch, dInfo);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return (int)cudaGetLastError();
+}
+
 template <typename T, int N, int CL, int WARPS, int MINB>
 int launch_gj_colsplit(StridedIO<T> io, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds) {
     using G = GjcGeo<T, N, CL, WARPS>;
@@ -348,6 +365,9 @@ int launch_tile_gp(GpIO<T> io, i64 batch, int *dInfo, cudaStream_t st, DeviceSta
 #define INVGPU_GJR_INSTANTIATE(T, N, ROWS, MINB) \
     template int invgpu::launch_gj_roll<T, N, ROWS, invgpu::StridedIO<T>, MINB>(invgpu::StridedIO<T>, int, invgpu::i64, int *, cudaStream_t, invgpu::DeviceState *); \
     template int invgpu::launch_gj_roll<T, N, ROWS, invgpu::PtrIO<T>, MINB>(invgpu::PtrIO<T>, int, invgpu::i64, int *, cudaStream_t, invgpu::DeviceState *);
+#define INVGPU_GJR2_INSTANTIATE(T, N, CW, MINB) \
+    template int invgpu::launch_gj_roll2d<T, N, CW, invgpu::StridedIO<T>, MINB>(invgpu::StridedIO<T>, int, invgpu::i64, int *, cudaStream_t, invgpu::DeviceState *); \
+    template int invgpu::launch_gj_roll2d<T, N, CW, invgpu::PtrIO<T>, MINB>(invgpu::PtrIO<T>, int, invgpu::i64, int *, cudaStream_t, invgpu::DeviceState *);
 #define INVGPU_GJC_INSTANTIATE(T, N, CL, WARPS, MINB) \
     template int invgpu::launch_gj_colsplit<T, N, CL, WARPS, MINB>(invgpu::StridedIO<T>, invgpu::i64, int *, cudaStream_t, invgpu::DeviceState *);
 #define INVGPU_GJT_INSTANTIATE(T, N, TR, TC, MINB) \

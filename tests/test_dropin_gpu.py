@@ -303,7 +303,7 @@ def test_mixed_scheduler_concurrent_streams_and_threads(api):
 
 
 # ------------------------------------------------------------------ ill-conditioned fp32 general inverse
-@pytest.mark.parametrize("n", [12, 16, 32, 64])
+@pytest.mark.parametrize("n", [12, 16, 32, 64, 72, 128])
 def test_general_inverse_ill_conditioned_fp32(api, n):
     """The lean lane = row kernels use rcp.approx + one Newton step and the multiplier form z = -a * r: on matrices
     with cond 1e4..1e5 the result must stay as close to the fp64 truth as the (division-based) oracle's."""

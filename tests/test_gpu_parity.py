@@ -252,8 +252,9 @@ def test_general_flags_match_oracle(api, dtype, n):
 @pytest.mark.parametrize("n", [40, 64, 100, 128])
 @pytest.mark.parametrize("dtype", DTYPES)
 def test_general_flags_tile_tiers(api, n, dtype):
-    """Orders above 32 run on the lane = row kernel with two rows per lane (fp32 up to 64) or on the 2-D register-tile
-    Gauss-Jordan kernel (gj_tile_kernels.cuh; fp32 n = 64 / 48 through INVGPU_GJ_KERNEL=tile below): flags are
+    """Orders above 32 run on the lane = row kernel with two rows per lane (fp32 up to 64), on the CTA-per-matrix rolled
+    kernel (gj_roll2d_kernels.cuh, fp32 65 .. 128) or on the 2-D register-tile Gauss-Jordan kernel (gj_tile_kernels.cuh: fp64;
+    fp32 n = 48 / 64 / 100 / 128 through INVGPU_GJ_KERNEL=tile below): flags are
     sgetrf's (first column without a non-zero pivot), a NaN column counts as singular, outputs of flagged
     matrices are NaN and the rest of the batch is unaffected."""
     rng = np.random.default_rng(n)
@@ -269,7 +270,7 @@ def test_general_flags_tile_tiers(api, n, dtype):
     good = info == 0
     assert_general_parity(a[good], orc.from_colmajor(got, n)[good], orc.from_colmajor(want, n)[good], dtype, f"flags n={n}")
     assert np.isnan(orc.from_colmajor(got, n)[~good]).all()
-    want_tier = "warp-rowlane" if (dtype == np.float32 and n <= 64) else "gj-tile"
+    want_tier = "warp-rowlane" if (dtype == np.float32 and n <= 64) else "cta-roll2d" if dtype == np.float32 else "gj-tile"
     assert api.tier_name("general", n, dtype).startswith(want_tier)
 
 
@@ -786,7 +787,8 @@ print("variant ok", err)
 
 @pytest.mark.parametrize("kernel,n,dtype", [("colsplit", 16, "float32"), ("colsplit", 32, "float32"), ("rowlane", 16, "float64"),
                                             ("rowlane", 32, "float64"), ("rowlane", 8, "float32"), ("rowlane", 24, "float32"),
-                                            ("generic", 32, "float32"), ("colsplit", 16, "float64"), ("tile", 32, "float64"), ("tile", 24, "float64"), ("tile", 64, "float32"), ("tile", 48, "float32")])
+                                            ("generic", 32, "float32"), ("colsplit", 16, "float64"), ("tile", 32, "float64"), ("tile", 24, "float64"), ("tile", 64, "float32"), ("tile", 48, "float32"),
+                                            ("tile", 128, "float32"), ("tile", 100, "float32")])
 def test_general_kernel_variants(kernel, n, dtype):
     """The general-inverse tiers that are not the default for a shape (INVGPU_GJ_KERNEL = colsplit: column-split lanes
     rowlane: lane = row also at n = 8, tile: the 2-D tile kernel also at 17 <= n <= 32, generic: shared-memory tier) keep their parity tests:

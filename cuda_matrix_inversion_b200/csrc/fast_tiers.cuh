@@ -166,6 +166,11 @@ template <typename T, typename TT> struct IOCast<PtrIO<T>, TT> { typedef PtrIO<T
         return launch_gj_roll2d<TT, N, CW, typename IOCast<IO, TT>::type, MINB>(                         \
             *reinterpret_cast<typename IOCast<IO, TT>::type *>(&io), n, batch, dInfo, st, ds);
 
+#define INVGPU_GJR2WS_TRY(TT, N, MINB)                                                              \
+    if (std::is_same<T, TT>::value && n <= N && gj_roll2d_ws_enabled())                              \
+        return launch_gj_roll2d_ws<TT, N, typename IOCast<IO, TT>::type, MINB>(                      \
+            *reinterpret_cast<typename IOCast<IO, TT>::type *>(&io), n, batch, dInfo, st, ds);
+
 // 2-D tile Gauss-Jordan: smallest instantiated padded order >= n wins (ascending lists)
 #define INVGPU_GJT_TRY(TT, N, TR, TC, MINB)                                                         \
     if (std::is_same<T, TT>::value && n <= N)                                                        \
@@ -198,7 +203,7 @@ static int fast_general(IO io, int n, i64 batch, int *dInfo, cudaStream_t st, De
         INVGPU_GJC_ALL(INVGPU_GJC_TRY)
     }
     if (use_roll) { INVGPU_GJR_ALL(INVGPU_GJR_TRY) }    // rolled lane = row kernel: every n <= 64 that the n = 8 TMA kernel did not take
-    if (which == 0 && sizeof(T) == 4 && n > 64) { INVGPU_GJR2_ALL(INVGPU_GJR2_TRY) }   // one CTA per matrix, rolled (fp32 65 .. 128)
+    if (which == 0 && sizeof(T) == 4 && n > 64) { INVGPU_GJR2WS_ALL(INVGPU_GJR2WS_TRY) INVGPU_GJR2_ALL(INVGPU_GJR2_TRY) }   // one CTA per matrix, rolled (fp32 65 .. 128)
     if (((which == 0 || which == 3) && n > INVGPU_GJT_MIN_N(T)) || (which == 4 && n > 16)) { INVGPU_GJT_ALL(INVGPU_GJT_TRY) }
     INVGPU_GJ_ALL(INVGPU_GJ_TRY)
     return INVGPU_NO_FAST_PATH;

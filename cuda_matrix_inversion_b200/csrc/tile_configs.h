@@ -121,6 +121,13 @@
 #endif
 #define INVGPU_GJR2_F32(X) X(float, 128, INVGPU_GJR2_CW, INVGPU_GJR2_MINB)
 #define INVGPU_GJR2_ALL(X) INVGPU_GJR2_F32(X)
+// the warp-specialised form (4 FMA warps + 1 pivot warp, setmaxnreg register hand-over, INVGPU_GJR2_WS=1):  X(T, N, MINB)
+// measured 4.60 ms against 4.21-4.26 ms of the four-warp kernel (profiles/r2_gj_roll2d_128_summary.md): lab builds only
+#ifndef INVGPU_GJR2WS_MINB
+#define INVGPU_GJR2WS_MINB 2
+#endif
+#define INVGPU_GJR2WS_F32(X) INVGPU_LAB_ONLY(X(float, 128, INVGPU_GJR2WS_MINB))
+#define INVGPU_GJR2WS_ALL(X) INVGPU_GJR2WS_F32(X)
 
 // SPD inverse, one-sweep Cholesky (onesweep_kernels.cuh), warp tiers:  X(T, N, TR, TC, STAGE, MINB)
 #ifndef INVGPU_OS_F32_N32_MINB

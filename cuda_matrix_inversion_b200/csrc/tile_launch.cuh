@@ -25,6 +25,16 @@ int launch_gj_roll(IO io, int n, i64 batch, int *dInfo, cudaStream_t st, DeviceS
 template <typename T, int N, int CW, typename IO, int MINB>
 int launch_gj_roll2d(IO io, int n, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds);
 
+// INVGPU_GJR2_WS=1 (lab builds) selects the warp-specialised kernel (4 FMA warps + a pivot warp) instead of the four-warp one
+static inline bool gj_roll2d_ws_enabled() {
+    static int on = -1;
+    if (on < 0) { const char *e = getenv("INVGPU_GJR2_WS"); on = (e && *e == '1') ? 1 : 0; }
+    return on != 0;
+}
+
+template <typename T, int N, typename IO, int MINB>
+int launch_gj_roll2d_ws(IO io, int n, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds);
+
 template <typename T, int N, int CL, int WARPS, int MINB>
 int launch_gj_colsplit(StridedIO<T> io, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds);
 
@@ -300,6 +310,19 @@ int launch_gj_roll2d(IO io, int n, i64 batch, int *dInfo, cudaStream_t st, Devic
     return (int)cudaGetLastError();
 }
 
+template <typename T, int N, typename IO, int MINB>
+int launch_gj_roll2d_ws(IO io, int n, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds) {
+    using G = GjRoll2dGeo<T, N, 32>;
+    auto kern = (n == N) ? gj_roll2d_ws_kernel<T, N, IO, MINB, true> : gj_roll2d_ws_kernel<T, N, IO, MINB, false>;
+    const size_t smem = (size_t)(G::WORDS + N) * sizeof(T);
+    int grid = 0;
+    int rc = persistent_grid(kern, 256, smem, batch, ds, &grid);
+    if (rc) return rc;
+    kern<<<grid, 256, smem, st>>>(io, n, batch, dInfo);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return (int)cudaGetLastError();
+}
+
 template <typename T, int N, int CL, int WARPS, int MINB>
 int launch_gj_colsplit(StridedIO<T> io, i64 batch, int *dInfo, cudaStream_t st, DeviceState *ds) {
     using G = GjcGeo<T, N, CL, WARPS>;
@@ -368,6 +391,9 @@ int launch_tile_gp(GpIO<T> io, i64 batch, int *dInfo, cudaStream_t st, DeviceSta
 #define INVGPU_GJR2_INSTANTIATE(T, N, CW, MINB) \
     template int invgpu::launch_gj_roll2d<T, N, CW, invgpu::StridedIO<T>, MINB>(invgpu::StridedIO<T>, int, invgpu::i64, int *, cudaStream_t, invgpu::DeviceState *); \
     template int invgpu::launch_gj_roll2d<T, N, CW, invgpu::PtrIO<T>, MINB>(invgpu::PtrIO<T>, int, invgpu::i64, int *, cudaStream_t, invgpu::DeviceState *);
+#define INVGPU_GJR2WS_INSTANTIATE(T, N, MINB) \
+    template int invgpu::launch_gj_roll2d_ws<T, N, invgpu::StridedIO<T>, MINB>(invgpu::StridedIO<T>, int, invgpu::i64, int *, cudaStream_t, invgpu::DeviceState *); \
+    template int invgpu::launch_gj_roll2d_ws<T, N, invgpu::PtrIO<T>, MINB>(invgpu::PtrIO<T>, int, invgpu::i64, int *, cudaStream_t, invgpu::DeviceState *);
 #define INVGPU_GJC_INSTANTIATE(T, N, CL, WARPS, MINB) \
     template int invgpu::launch_gj_colsplit<T, N, CL, WARPS, MINB>(invgpu::StridedIO<T>, invgpu::i64, int *, cudaStream_t, invgpu::DeviceState *);
 #define INVGPU_GJT_INSTANTIATE(T, N, TR, TC, MINB) \

@@ -805,3 +805,23 @@ def test_general_kernel_variants(kernel, n, dtype):
                        env=env, capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stdout + p.stderr
     assert "variant ok" in p.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [128, 100])
+def test_general_warp_specialised_variant(n):
+    """INVGPU_GJR2_WS=1 (lab builds): the warp-specialised form of the CTA-per-matrix Gauss-Jordan kernel -- four FMA warps plus a
+    pivot warp, registers handed over with setmaxnreg (gj_roll2d_ws_kernel).  Measured slower than the four-warp kernel, kept
+    with the same parity test: oracle parity, sgetrf flags, ragged tail."""
+    import subprocess
+    import sys
+    from cuda_matrix_inversion_b200 import lib
+    if not lib.invgpu_has_lab():
+        pytest.skip("non-default kernel generation: built only with `make lab=1`")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, INVGPU_GJR2_WS="1")
+    p = subprocess.run([sys.executable, "-c", _GJ_VARIANT_SNIPPET.format(root=root, n=n, batch=331, dtype="float32", tol=1e-4)],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert "variant ok" in p.stdout
+

@@ -49,6 +49,9 @@ struct GjRoll2dGeo {
 // A register pair as ONE 64-bit value.  Held as two floats (GjPair) the halves of a pair drifted apart in the register
 // allocation of this kernel -- ptxas re-assembled every FFMA2 operand with two moves (355 moves for 128 FFMA2 per loop
 // iteration); a .b64 virtual register is an aligned pair by construction.
+#ifndef GJ2D_OWNER_ONLY_ROTATION
+#define GJ2D_OWNER_ONLY_ROTATION 1
+#endif
 typedef unsigned long long P64;
 __device__ __forceinline__ P64 p64_pack(float x, float y) { P64 p; asm("mov.b64 %0, {%1, %2};" : "=l"(p) : "f"(x), "f"(y)); return p; }
 __device__ __forceinline__ float p64_lo(P64 p) { float x, y; asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(p)); return x; }
@@ -129,7 +132,9 @@ __device__ __forceinline__ void gj2d_step(P64 (&ap)[N / 32][CW / 2], T *zline, T
     }
     __syncthreads();
     const ulonglong2 *pr = reinterpret_cast<const ulonglong2 *>(rowline + G::CW * w);   // two pairs per 128-bit broadcast load
-    if (!B) {
+    // Only the OWNER warp moves its window (it needs its pivot column at position 0; 32 pivots = one full turn, so the window is
+    // in natural order whenever ownership changes hands); the other warps update in place.
+    if (!B || (GJ2D_OWNER_ONLY_ROTATION && w != k / CW)) {
         #pragma unroll
         for (int i2 = 0; i2 < H; i2 += 2) {
             const ulonglong2 rr = pr[i2 / 2];

@@ -554,16 +554,28 @@ static int run_mixed_spd(T *const *hIn, T *const *hOut, const int *hN, i64 count
     // work list + tickets of THIS call: the next buffer of a small ring; it is free again when the event recorded
     // behind the last tier kernel of the call that used it before has completed (calls on other streams or from
     // other host threads therefore never overwrite a list that kernels still read)
-    // prefer a buffer that is free already and large enough (no allocation, no wait); then any free one; only when all are
-    // in flight wait for the oldest.  (Plain round robin made the first kMixedRing calls allocate pinned memory each: with
-    // eight ranks pinning at once that cost tens of milliseconds per call on the 8-GPU box.)
-    int pick = -1;
-    for (int i = 0; i < DeviceState::kMixedRing && pick < 0; ++i)
-        if (ds->mixed[i].bytes >= need && cudaEventQuery(ds->mixed[i].done) == cudaSuccess) pick = i;
-    for (int i = 0; i < DeviceState::kMixedRing && pick < 0; ++i)
-        if (cudaEventQuery(ds->mixed[i].done) == cudaSuccess) pick = i;
+    // 1. a buffer that is free already and large enough (no allocation, no wait);
+    // 2. while fewer than two large-enough buffers exist: a free slot, which gets allocated (two lists are enough to plan call
+    //    i + 1 while the kernels of call i run -- the list of call i - 1 is free by then);
+    // 3. otherwise WAIT for the large-enough buffer used longest ago instead of pinning another one.
+    // (Plain round robin made the first kMixedRing calls pin memory each -- tens of milliseconds per call with eight ranks
+    // pinning at once; "any free slot" still pinned a third and fourth list inside a back-to-back timed loop: 40 ms per step
+    // instead of 22 in one 4-GPU bench run.)
+    int pick = -1, big = 0;
+    for (int i = 0; i < DeviceState::kMixedRing; ++i) {
+        if (ds->mixed[i].bytes < need) continue;
+        ++big;
+        if (pick < 0 && cudaEventQuery(ds->mixed[i].done) == cudaSuccess) pick = i;
+    }
+    if (pick < 0 && big < 2)
+        for (int i = 0; i < DeviceState::kMixedRing && pick < 0; ++i)
+            if (ds->mixed[i].bytes < need && cudaEventQuery(ds->mixed[i].done) == cudaSuccess) pick = i;
+    if (pick < 0 && big > 0)
+        for (int i = 0; i < DeviceState::kMixedRing; ++i)
+            if (ds->mixed[i].bytes >= need && (pick < 0 || ds->mixed[i].seq < ds->mixed[pick].seq)) pick = i;
     cudaGetLastError();                                       // cudaErrorNotReady of the queries is not an error
-    if (pick < 0) pick = (int)(ds->mixed_next++ % DeviceState::kMixedRing);
+    if (pick < 0) pick = (int)(ds->mixed_next % DeviceState::kMixedRing);
+    ds->mixed[pick].seq = ++ds->mixed_next;
     DeviceState::MixedBuf &mb = ds->mixed[pick];
     INVGPU_TRY(cudaEventSynchronize(mb.done));
     if (mb.bytes < need) {

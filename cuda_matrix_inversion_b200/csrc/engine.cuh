@@ -49,7 +49,7 @@ struct DeviceState {
     // work lists of the mixed-dimension scheduler: a ring of (device copy + pinned staging) pairs, each guarded by
     // the event recorded after the LAST tier kernel that reads it
     static const int kMixedRing = 4;
-    struct MixedBuf { void *d = nullptr, *h = nullptr; size_t bytes = 0; cudaEvent_t done = nullptr, uploaded = nullptr; };
+    struct MixedBuf { void *d = nullptr, *h = nullptr; size_t bytes = 0; cudaEvent_t done = nullptr, uploaded = nullptr; unsigned long long seq = 0; };
     MixedBuf mixed[kMixedRing];
     unsigned mixed_next = 0;
     // one lock per device: the host pipeline and the mixed scheduler of different devices run concurrently

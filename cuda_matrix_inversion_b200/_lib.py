@@ -26,6 +26,7 @@ def _load() -> C.CDLL:
         "invgpu_version": (C.c_char_p, []),
         "invgpu_device_count": (_int, []),
         "invgpu_has_lab": (_int, []),
+        "invgpu_gp_upper_h2d": (_int, [_int, _int]),
         "invgpu_set_device": (_int, [_int]),
         "invgpu_error_string": (C.c_char_p, [_int]),
         "invgpu_launch_count": (_i64, []),

@@ -180,7 +180,37 @@ struct HostArr {
     size_t unit;        // bytes per batch unit
     bool pinned;
     size_t off;         // offset of this array inside a slot
+    int tri_n = 0;      // > 0: units are column-major tri_n x tri_n matrices of which the kernel reads the UPPER triangle only
+    size_t tri_esz = 0; //      (element size): the host -> device copy sends the column prefixes, not the whole matrices
 };
+
+// Host -> device copy of `cnt` column-major n x n matrices of which only the upper triangle (rows 0 .. c of column c) is needed:
+// the columns are taken in groups of W, group g sends rows 0 .. (g + 1) W - 1 of its columns with ONE strided copy over all
+// matrices of the chunk (a 3-D copy: x = the column prefix, y = the W columns of the group, z = the matrices).  The copy
+// engine moves strided rows of >= 128 bytes at the full 55 GB/s of useful bytes (tools/probe_2d.py on B200: 512 / 384 / 256 /
+// 128 / 64-byte rows at a 512-byte pitch: 55.6 / 54.0 / 55.5 / 51.3 / 27.8 GB/s); an n = 128 fp32 batch sends 62.5 % of the
+// bytes (W = 32: rows of 128 .. 512 bytes).
+static cudaError_t h2d_upper_triangle(char *dst, const char *src, int n, size_t esz, i64 cnt, cudaStream_t st) {
+    // columns per group (INVGPU_GP_UPPER_W).  Measured end to end, 100 000 x 128x128 fp32 on one B200 (tools/gp_e2e.py): whole
+    // matrices 8.05e5 eval/s; W = 8 / 16 / 32 / 64: 9.3e5 / 1.12e6 / 1.17e6 / 1.04e6 (128 MiB chunks: 1.20e6)
+    static int W = 0;
+    if (W == 0) { const char *e = getenv("INVGPU_GP_UPPER_W"); W = (e && atoi(e) > 0) ? atoi(e) : 32; }
+    for (int g = 0; g * W < n; ++g) {
+        const int cols = (g + 1) * W <= n ? W : n - g * W;
+        const size_t rows = (size_t)std::min(n, (g + 1) * W);
+        cudaMemcpy3DParms p;
+        memset(&p, 0, sizeof(p));
+        p.srcPtr = make_cudaPitchedPtr((void *)src, (size_t)n * esz, (size_t)n * esz, (size_t)n);
+        p.dstPtr = make_cudaPitchedPtr((void *)dst, (size_t)n * esz, (size_t)n * esz, (size_t)n);
+        p.srcPos = make_cudaPos(0, (size_t)g * W, 0);
+        p.dstPos = make_cudaPos(0, (size_t)g * W, 0);
+        p.extent = make_cudaExtent(rows * esz, (size_t)cols, (size_t)cnt);
+        p.kind = cudaMemcpyHostToDevice;
+        cudaError_t e = cudaMemcpy3DAsync(&p, st);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
 
 static bool is_pinned(const void *p) {
     cudaPointerAttributes a;
@@ -397,7 +427,8 @@ static int host_pipeline(std::vector<HostArr> &arrs, i64 batch, int *info, int *
             if (!a.in) continue;
             const char *src = a.in + (size_t)first * a.unit;
             if (!a.pinned) { staging_copy(hbase + a.off, src, (size_t)cnt * a.unit); src = hbase + a.off; }
-            INVGPU_PIPE_TRY(cudaMemcpyAsync(dbase + a.off, src, (size_t)cnt * a.unit, cudaMemcpyHostToDevice, ds->s_in));
+            if (a.tri_n > 0) INVGPU_PIPE_TRY(h2d_upper_triangle(dbase + a.off, src, a.tri_n, a.tri_esz, cnt, ds->s_in));
+            else INVGPU_PIPE_TRY(cudaMemcpyAsync(dbase + a.off, src, (size_t)cnt * a.unit, cudaMemcpyHostToDevice, ds->s_in));
         }
         stamp(ds->s_in);
         INVGPU_PIPE_TRY(cudaEventRecord(ds->ev_in[slot], ds->s_in));
@@ -447,6 +478,16 @@ static int host_inverse(const T *As, T *aInvs, int n, i64 batch, int *info, int 
     });
 }
 
+// The tcgen05 tier (fp32, n = 128) reads the upper triangle of B only (poisoned-lower-triangle test in tests/test_gpu_parity.py):
+// the host call sends the column prefixes.  INVGPU_GP_UPPER_H2D=0 sends whole matrices; so does any INVGPU_GP_KERNEL override
+// (other tiers).
+static bool gp_upper_h2d(int n, int dtype_bytes) {
+    if (dtype_bytes != 4 || n != 128) return false;
+    static int upper = -1;
+    if (upper < 0) { const char *e = getenv("INVGPU_GP_UPPER_H2D"); upper = ((e && *e == '0') || getenv("INVGPU_GP_KERNEL")) ? 0 : 1; }
+    return upper == 1;
+}
+
 template <typename T>
 static int host_gp(int n, const T *As, const T *Bs, const T *Cs, const T *Ds, const T *Es, T *Means, T *Vars,
                    i64 batch, int *info, int *first_bad) {
@@ -457,6 +498,7 @@ static int host_gp(int n, const T *As, const T *Bs, const T *Cs, const T *Ds, co
     arrs.push_back(HostArr{(const char *)As, nullptr, (size_t)n * sizeof(T), false, 0});
     arrs.push_back(HostArr{(const char *)Bs, nullptr, (size_t)n * n * sizeof(T), false, 0});
     arrs.push_back(HostArr{(const char *)Cs, nullptr, (size_t)n * sizeof(T), false, 0});
+    if (gp_upper_h2d(n, (int)sizeof(T))) { arrs[1].tri_n = n; arrs[1].tri_esz = sizeof(T); }   // send the column prefixes of B only
     int iD = -1, iE = -1, iM = -1, iV = -1;
     if (Means) { iD = (int)arrs.size(); arrs.push_back(HostArr{(const char *)Ds, nullptr, (size_t)n * sizeof(T), false, 0}); }
     if (Vars)  { iE = (int)arrs.size(); arrs.push_back(HostArr{(const char *)Es, nullptr, sizeof(T), false, 0}); }
@@ -674,6 +716,7 @@ extern "C" {
 
 const char *invgpu_version(void) { return INVGPU_LAB ? "invgpu 0.2 (sm_100a, +lab)" : "invgpu 0.2 (sm_100a)"; }
 int invgpu_has_lab(void) { return INVGPU_LAB; }
+int invgpu_gp_upper_h2d(int n, int dtype_bytes) { return gp_upper_h2d(n, dtype_bytes) ? 1 : 0; }
 
 int invgpu_device_count(void) {
     int n = 0;

@@ -418,3 +418,40 @@ def test_legacy_lu_device_leaves_factors_in_devAs(api):
     lu_o, _, _ = orc.getrf(flat, n)
     assert normwise_err(orc.from_colmajor(d_a.cpu().numpy(), n), orc.from_colmajor(lu_o, n)) <= 1e-4
     assert residual_inf(a, orc.from_colmajor(d_inv.cpu().numpy(), n)) <= 1e-4
+
+
+# ------------------------------------------------------------------ GP host call: only the upper triangle of B crosses the bus
+def test_gp_host_sends_upper_triangle_only(api):
+    """invgpu_gp_host_f32 at n = 128 (tcgen05 tier) sends the column prefixes of B (strided 3-D copies, capi.cu
+    h2d_upper_triangle) instead of whole matrices.  Several pipeline chunks + a ragged tail, pinned and pageable B: the result
+    must be bit-identical to the device-resident call on the full matrices, and a B whose strictly lower triangle is NaN on the
+    host must give the same answer (the lower triangle is neither read nor needed)."""
+    import torch
+    from cuda_matrix_inversion_b200 import lib
+    n, batch = 128, 1337                                           # 32 MiB chunks hold ~ 500 evaluations: three chunks
+    assert lib.invgpu_gp_upper_h2d(n, 4) == 1 and lib.invgpu_gp_upper_h2d(64, 4) == 0 and lib.invgpu_gp_upper_h2d(n, 8) == 0
+    rng = np.random.default_rng(21)
+    r = rng.random((batch, n, n), dtype=np.float32)
+    b = r + r.transpose(0, 2, 1) + n * np.eye(n, dtype=np.float32)
+    a, c, d = (rng.random((batch, n), dtype=np.float32) for _ in range(3))
+    flat_b = orc.to_colmajor(b)
+    # device-resident reference run on whole matrices
+    tb, ta, tc, td = (torch.from_numpy(x.reshape(-1).copy()).cuda() for x in (flat_b, a, c, d))
+    out_m = torch.zeros(batch, device="cuda")
+    d_info = torch.zeros(batch, dtype=torch.int32, device="cuda")
+    api.gp_device(n, ta.data_ptr(), tb.data_ptr(), tc.data_ptr(), td.data_ptr(), 0, out_m.data_ptr(), 0, batch, np.float32,
+                  d_info.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    want = out_m.cpu().numpy()
+    assert int(d_info.abs().max()) == 0
+    # host call, pageable B (staged through the ring) and pinned B, lower triangle poisoned on the host
+    poisoned = flat_b.reshape(batch, n, n).copy()                  # [matrix, column, row]
+    ci, ri = np.arange(n).reshape(n, 1), np.arange(n).reshape(1, n)
+    poisoned[:, ri > ci] = np.nan
+    for name, hb in (("pageable", poisoned.reshape(-1)), ("pinned", torch.from_numpy(poisoned.reshape(-1)).pin_memory().numpy())):
+        means, _, info = api.gp_host(n, a.reshape(-1), hb, c.reshape(-1), Ds=d.reshape(-1))
+        assert not info.any(), name
+        assert np.array_equal(means, want), (name, np.abs(means - want).max())
+    om, _ = orc.gp_mean(n, a.reshape(-1)[: 8 * n], flat_b[: 8 * n * n], c.reshape(-1)[: 8 * n], d.reshape(-1)[: 8 * n])
+    assert np.abs(want[:8] - om).max() <= 1e-4
+

@@ -193,8 +193,10 @@ struct HostArr {
 static cudaError_t h2d_upper_triangle(char *dst, const char *src, int n, size_t esz, i64 cnt, cudaStream_t st) {
     // columns per group (INVGPU_GP_UPPER_W).  Measured end to end, 100 000 x 128x128 fp32 on one B200 (tools/gp_e2e.py): whole
     // matrices 8.05e5 eval/s; W = 8 / 16 / 32 / 64: 9.3e5 / 1.12e6 / 1.17e6 / 1.04e6 (128 MiB chunks: 1.20e6)
-    static int W = 0;
-    if (W == 0) { const char *e = getenv("INVGPU_GP_UPPER_W"); W = (e && atoi(e) > 0) ? atoi(e) : 32; }
+    // default: the shortest row is 128 bytes (32 fp32 / 16 fp64 columns per group)
+    static int w_env = -1;
+    if (w_env < 0) { const char *e = getenv("INVGPU_GP_UPPER_W"); w_env = (e && atoi(e) > 0) ? atoi(e) : 0; }
+    const int W = w_env > 0 ? w_env : (int)(128 / esz);
     for (int g = 0; g * W < n; ++g) {
         const int cols = (g + 1) * W <= n ? W : n - g * W;
         const size_t rows = (size_t)std::min(n, (g + 1) * W);
@@ -478,11 +480,11 @@ static int host_inverse(const T *As, T *aInvs, int n, i64 batch, int *info, int 
     });
 }
 
-// The tcgen05 tier (fp32, n = 128) reads the upper triangle of B only (poisoned-lower-triangle test in tests/test_gpu_parity.py):
-// the host call sends the column prefixes.  INVGPU_GP_UPPER_H2D=0 sends whole matrices; so does any INVGPU_GP_KERNEL override
-// (other tiers).
+// Every GP tier reads the upper triangle of B only (tests/test_gpu_parity.py::test_gp_reads_upper_triangle_only poisons the
+// lower one, all tiers, both dtypes), so the host call sends the column prefixes wherever a column is at least two 128-byte
+// rows long.  INVGPU_GP_UPPER_H2D=0 sends whole matrices; so does any INVGPU_GP_KERNEL override (non-default tiers).
 static bool gp_upper_h2d(int n, int dtype_bytes) {
-    if (dtype_bytes != 4 || n != 128) return false;
+    if ((size_t)n * (size_t)dtype_bytes < 256) return false;
     static int upper = -1;
     if (upper < 0) { const char *e = getenv("INVGPU_GP_UPPER_H2D"); upper = ((e && *e == '0') || getenv("INVGPU_GP_KERNEL")) ? 0 : 1; }
     return upper == 1;

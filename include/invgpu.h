@@ -44,7 +44,7 @@ const char *invgpu_version(void);
  * environment knobs are present (see csrc/tile_configs.h); 0 in a default build, where those knobs fall back to the defaults. */
 int invgpu_has_lab(void);
 /* 1 when invgpu_gp_host_* sends only the column prefixes (upper triangle) of the n x n matrices B for this order and element
- * size (the kernel tier that serves the shape never reads the rest; INVGPU_GP_UPPER_H2D=0 turns it off): what callers that
+ * size (columns of at least 256 bytes; no GP tier reads the rest; INVGPU_GP_UPPER_H2D=0 turns it off): what callers that
  * account bytes on the bus need to know (bench.py). */
 int invgpu_gp_upper_h2d(int n, int dtype_bytes);
 int invgpu_device_count(void);                 /* 0 when no CUDA device is usable */

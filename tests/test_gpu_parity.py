@@ -825,3 +825,35 @@ def test_general_warp_specialised_variant(n):
     assert p.returncode == 0, p.stdout + p.stderr
     assert "variant ok" in p.stdout
 
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("n", [8, 16, 24, 32, 64, 100, 128, 160])
+def test_gp_reads_upper_triangle_only(api, n, dtype):
+    """Every GP tier (thread-per-evaluation, tile, sweep, tcgen05, shared-memory generic) reads only the UPPER triangle of B
+    (rows 0 .. c of column c; the reference's CPU code does the same: potrf 'U', src/gauss_cpu.c:54): a batch whose strictly
+    lower triangle is NaN gives bit-identical means and variances.  This is what lets the host call send column prefixes."""
+    import torch
+    tdt = torch.float32 if dtype == np.float32 else torch.float64
+    batch = 300
+    gen = torch.Generator(device="cuda").manual_seed(n)
+    r = torch.rand((batch, n, n), generator=gen, device="cuda", dtype=tdt)
+    colmajor = (r + r.transpose(1, 2) + n * torch.eye(n, device="cuda", dtype=tdt)).contiguous()    # symmetric: [c, r] == [r, c]
+    a, c, d = (torch.rand((batch, n), generator=gen, device="cuda", dtype=tdt) for _ in range(3))
+    e = torch.rand(batch, generator=gen, device="cuda", dtype=tdt)
+    ci, ri = torch.arange(n, device="cuda").view(n, 1), torch.arange(n, device="cuda").view(1, n)
+    poisoned = colmajor.clone()
+    poisoned[:, ri > ci] = float("nan")                            # [c, r] with r > c: strictly lower triangle
+    st = torch.cuda.current_stream().cuda_stream
+    outs = []
+    for bmat in (colmajor, poisoned):
+        m, v = torch.zeros(batch, device="cuda", dtype=tdt), torch.zeros(batch, device="cuda", dtype=tdt)
+        info = torch.full((batch,), -1, dtype=torch.int32, device="cuda")
+        api.gp_device(n, a.data_ptr(), bmat.data_ptr(), c.data_ptr(), d.data_ptr(), e.data_ptr(), m.data_ptr(), v.data_ptr(),
+                      batch, dtype, info.data_ptr(), st)
+        torch.cuda.synchronize()
+        assert int(info.abs().max()) == 0
+        outs.append((m.cpu().numpy(), v.cpu().numpy()))
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1]), api.tier_name("gp", n, dtype)
+    assert np.isfinite(outs[1][0]).all() and np.isfinite(outs[1][1]).all()
+

@@ -22,4 +22,4 @@ step()
 ts = []
 for _ in range(3):
     t0 = time.perf_counter(); step(); ts.append(time.perf_counter() - t0)
-print(f"W={os.environ.get('INVGPU_GP_UPPER_W', '16')} upper={lib.invgpu_gp_upper_h2d(n, 4)} chunk={os.environ.get('INVGPU_CHUNK_MB', '32')}MB: {gb / min(ts):.4e} eval/s  ({min(ts) * 1e3:.1f} ms, info max {int(np.abs(info).max())}, checksum {float(means.sum()):.6e})")
+print(f"W={os.environ.get('INVGPU_GP_UPPER_W', 'default')} upper={lib.invgpu_gp_upper_h2d(n, 4)} chunk={os.environ.get('INVGPU_CHUNK_MB', '32')}MB: {gb / min(ts):.4e} eval/s  ({min(ts) * 1e3:.1f} ms, info max {int(np.abs(info).max())}, checksum {float(means.sum()):.6e})")

@@ -473,6 +473,9 @@ static int host_inverse(const T *As, T *aInvs, int n, i64 batch, int *info, int 
     std::vector<HostArr> arrs(2);
     arrs[0] = HostArr{(const char *)As, nullptr, (size_t)n * n * sizeof(T), false, 0};
     arrs[1] = HostArr{nullptr, (char *)aInvs, (size_t)n * n * sizeof(T), false, 0};
+    // (The SPD kernels read the upper triangle only as well, but sending column prefixes does not pay here: the inverse comes back
+    // as whole matrices and the two directions share the host path -- measured with tools/spd_e2e.py: n = 64 / 128 unchanged at
+    // 90 GB/s both ways, n = 32 (rows of 64 / 128 bytes) 1.13e7 -> 7.8e6 inv/s.)
     return host_pipeline(arrs, batch, info, first_bad, [&](void **d, i64 cnt, cudaStream_t st) -> int {
         StridedIO<T> io = dense_io<T>((const T *)d[0], (T *)d[1], n);
         if (SPD) return run_spd<T, StridedIO<T>, SPD_INVERSE>(io, n, cnt, (int *)d[2], st);

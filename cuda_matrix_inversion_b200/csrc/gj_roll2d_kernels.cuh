@@ -11,11 +11,12 @@
 //  * warp w owns the 32 natural columns 32 w .. 32 w + 31, lane l owns the ROWS = N / 32 consecutive rows ROWS l ..: a
 //    thread holds ROWS x 32 elements as horizontal FFMA2 pairs.  Per pivot it needs ROWS multipliers (one 128-bit load) and
 //    the 32 pivot-row entries of its columns (eight 128-bit broadcast loads, warp-uniform address) for 16 ROWS FFMA2.
-//  * ROTATING WINDOW (as gj_roll_kernels.cuh): every warp's 32-column window moves down one register per pivot -- the FMA
-//    destination simply is the neighbouring register, two pivots per loop iteration keep the pairs aligned -- so the pivot
-//    column of the owner warp is always register pair 0 and the loop body is two step bodies for any N.  The window is
-//    cyclic: position 0 re-enters at position 31, which in the owner warp is exactly where the new inverse column belongs;
-//    after N steps (N / 32 full turns) every window is back in natural order.
+//  * ROTATING WINDOW (as gj_roll_kernels.cuh): the OWNER warp's 32-column window moves down one register per pivot -- the FMA
+//    destination simply is the neighbouring register, two pivots per loop iteration keep the pairs aligned -- so its pivot
+//    column is always register pair 0 and the loop body is two step bodies for any N.  The window is cyclic: position 0
+//    re-enters at position 31, exactly where the new inverse column belongs; a warp owns 32 consecutive pivots = one full
+//    turn, so every window is in natural order whenever ownership changes hands and at the end.  The other warps update in
+//    place (GJ2D_OWNER_ONLY_ROTATION; rotating all of them measured the same at n = 128, 7 % slower padded).
 //  * ONE uniform update for everything:  a_ic += z_i * row_c  with  z_i = -a_ik / pivot  (z = 0 in the pivot row: rows are
 //    never scaled inside the loop, each is multiplied once at the end by the reciprocal of its own pivot).  The owner warp
 //    restarts its pivot column as e_p (1 in the pivot row, 0 elsewhere) BEFORE the pivot row is published, so the published

@@ -26,8 +26,10 @@ One JSON line on stdout (rank 0):
             OpenBLAS 0.3.15) on a bounded sample, all host cores
   gp_mean_128   the metric's second term (BASELINE configs[3]) at every N: 200 000 x 128x128 fp32 fused GP means
             sharded over the ranks (strong scaling) + the final all_gather of the scalars, with its own
-            roofline ((n^2+3n+1) sizeof(T) per evaluation), e2e through invgpu_gp_host_f32 and cpu_baseline
-            (calcluateMeanCPU, src/gauss_cpu.c:23)
+            roofline ((n^2+3n+1) sizeof(T) per evaluation), e2e through invgpu_gp_host_f32 (which sends only the upper-triangle
+            column prefixes of B: h2d_bytes_per_step counts what crosses the bus, h2d_bytes_whole_matrices the dense layout;
+            `ceiling` = a contiguous copy of the sent bytes, `whole_matrix_copy_value` = a copy of whole matrices) and
+            cpu_baseline (calcluateMeanCPU, src/gauss_cpu.c:23)
   mixed     BASELINE configs[4] at every N: 500 000 mixed-dimension matrices per GPU (4 M on 8 GPUs)
   extra     (N = 1 only) the other shapes, kernel-only, for context -- not part of the contract
 """

@@ -190,13 +190,16 @@ struct HostArr {
 // engine moves strided rows of >= 128 bytes at the full 55 GB/s of useful bytes (tools/probe_2d.py on B200: 512 / 384 / 256 /
 // 128 / 64-byte rows at a 512-byte pitch: 55.6 / 54.0 / 55.5 / 51.3 / 27.8 GB/s); an n = 128 fp32 batch sends 62.5 % of the
 // bytes (W = 32: rows of 128 .. 512 bytes).
-static cudaError_t h2d_upper_triangle(char *dst, const char *src, int n, size_t esz, i64 cnt, cudaStream_t st) {
-    // columns per group (INVGPU_GP_UPPER_W).  Measured end to end, 100 000 x 128x128 fp32 on one B200 (tools/gp_e2e.py): whole
-    // matrices 8.05e5 eval/s; W = 8 / 16 / 32 / 64: 9.3e5 / 1.12e6 / 1.17e6 / 1.04e6 (128 MiB chunks: 1.20e6)
+static int upper_group_width(size_t esz) {
     // default: the shortest row is 128 bytes (32 fp32 / 16 fp64 columns per group)
     static int w_env = -1;
     if (w_env < 0) { const char *e = getenv("INVGPU_GP_UPPER_W"); w_env = (e && atoi(e) > 0) ? atoi(e) : 0; }
-    const int W = w_env > 0 ? w_env : (int)(128 / esz);
+    return w_env > 0 ? w_env : (int)(128 / esz);
+}
+static cudaError_t h2d_upper_triangle(char *dst, const char *src, int n, size_t esz, i64 cnt, cudaStream_t st) {
+    // columns per group (INVGPU_GP_UPPER_W).  Measured end to end, 100 000 x 128x128 fp32 on one B200 (tools/gp_e2e.py): whole
+    // matrices 8.05e5 eval/s; W = 8 / 16 / 32 / 64: 9.3e5 / 1.12e6 / 1.17e6 / 1.04e6 (128 MiB chunks: 1.20e6)
+    const int W = upper_group_width(esz);
     for (int g = 0; g * W < n; ++g) {
         const int cols = (g + 1) * W <= n ? W : n - g * W;
         const size_t rows = (size_t)std::min(n, (g + 1) * W);
@@ -299,6 +302,35 @@ static void staging_copy(void *dst, const void *src, size_t bytes) {
         pool.emplace_back([=] { memcpy((char *)dst + off, (const char *)src + off, std::min(part, bytes - off)); });
     }
     memcpy(dst, src, std::min(part, bytes));
+    for (auto &th : pool) th.join();
+}
+
+// The same for `cnt` column-major n x n matrices of which only the upper triangle is needed (h2d_upper_triangle below sends
+// exactly these bytes on): column c is copied up to the end of its W-column group, (floor(c / W) + 1) W rows.
+static void staging_copy_upper(char *dst, const char *src, int n, size_t esz, long long cnt, int W) {
+    static int nthr = -1;
+    if (nthr < 0) {
+        const char *e = getenv("INVGPU_STAGE_THREADS");
+        nthr = e ? atoi(e) : 4;
+        const int hw = (int)std::thread::hardware_concurrency();
+        if (hw > 0 && nthr > hw) nthr = hw;
+        if (nthr < 1) nthr = 1;
+    }
+    auto part = [=](long long m0, long long m1) {
+        const size_t col = (size_t)n * esz;
+        for (long long m = m0; m < m1; ++m) {
+            const size_t base = (size_t)m * n * col;
+            for (int c = 0; c < n; ++c) {
+                const size_t rows = (size_t)std::min(n, (c / W + 1) * W);
+                memcpy(dst + base + (size_t)c * col, src + base + (size_t)c * col, rows * esz);
+            }
+        }
+    };
+    const int use = (int)std::min<long long>(nthr, std::max<long long>(1, cnt / 16));
+    if (use <= 1) { part(0, cnt); return; }
+    std::vector<std::thread> pool;
+    for (int t = 1; t < use; ++t) pool.emplace_back(part, cnt * t / use, cnt * (t + 1) / use);
+    part(0, cnt / use);
     for (auto &th : pool) th.join();
 }
 
@@ -428,7 +460,11 @@ static int host_pipeline(std::vector<HostArr> &arrs, i64 batch, int *info, int *
         for (auto &a : arrs) {
             if (!a.in) continue;
             const char *src = a.in + (size_t)first * a.unit;
-            if (!a.pinned) { staging_copy(hbase + a.off, src, (size_t)cnt * a.unit); src = hbase + a.off; }
+            if (!a.pinned) {
+                if (a.tri_n > 0) staging_copy_upper(hbase + a.off, src, a.tri_n, a.tri_esz, cnt, upper_group_width(a.tri_esz));
+                else staging_copy(hbase + a.off, src, (size_t)cnt * a.unit);
+                src = hbase + a.off;
+            }
             if (a.tri_n > 0) INVGPU_PIPE_TRY(h2d_upper_triangle(dbase + a.off, src, a.tri_n, a.tri_esz, cnt, ds->s_in));
             else INVGPU_PIPE_TRY(cudaMemcpyAsync(dbase + a.off, src, (size_t)cnt * a.unit, cudaMemcpyHostToDevice, ds->s_in));
         }

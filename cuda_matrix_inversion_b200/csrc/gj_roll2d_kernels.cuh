@@ -50,6 +50,9 @@ struct GjRoll2dGeo {
 // A register pair as ONE 64-bit value.  Held as two floats (GjPair) the halves of a pair drifted apart in the register
 // allocation of this kernel -- ptxas re-assembled every FFMA2 operand with two moves (355 moves for 128 FFMA2 per loop
 // iteration); a .b64 virtual register is an aligned pair by construction.
+#ifndef GJ2D_TWO_REDUX
+#define GJ2D_TWO_REDUX 1
+#endif
 #ifndef GJ2D_OWNER_ONLY_ROTATION
 #define GJ2D_OWNER_ONLY_ROTATION 1
 #endif
@@ -97,6 +100,21 @@ __device__ __forceinline__ void gj2d_step(P64 (&ap)[N / 32][CW / 2], T *zline, T
             mykey = max(mykey, key[q]);
         }
         const unsigned mx = __reduce_max_sync(0xffffffffu, mykey);
+#if GJ2D_TWO_REDUX
+        // second reduction: the smallest candidate row (first maximum in row order, like isamax / the oracle) together with the
+        // sign of its value -- (row << 1 | sign), the row dominates the order -- so neither ballots nor a shuffle of the pivot
+        // value are needed: |pivot| is mx itself
+        unsigned cand = 0xffffffffu;
+        #pragma unroll
+        for (int q = 0; q < ROWS; ++q) {
+            const unsigned code = ((unsigned)(ROWS * lane + q) << 1) | (__float_as_uint(v[q]) >> 31);
+            cand = (!((pivoted >> q) & 1u) && key[q] == mx) ? min(cand, code) : cand;
+        }
+        const unsigned best = __reduce_min_sync(0xffffffffu, cand);
+        const int prow = (int)(best >> 1);
+        const int pl = prow / ROWS, pq = prow % ROWS;
+        const T r = fast_rcp<T>(__uint_as_float(mx | (best << 31)));
+#else
         int prow = 1 << 30;                                        // first maximum in row order (row = ROWS lane + q)
         #pragma unroll
         for (int q = 0; q < ROWS; ++q) {
@@ -108,6 +126,7 @@ __device__ __forceinline__ void gj2d_step(P64 (&ap)[N / 32][CW / 2], T *zline, T
         #pragma unroll
         for (int q = 1; q < ROWS; ++q) mine = (pq == q) ? v[q] : mine;
         const T r = fast_rcp<T>(__shfl_sync(0xffffffffu, mine, pl));
+#endif
         T z[ROWS];
         #pragma unroll
         for (int q = 0; q < ROWS; ++q) {

@@ -111,7 +111,7 @@
 #define INVGPU_GJR_ALL(X) INVGPU_GJR_F32(X) INVGPU_GJR_F64(X)
 
 // one CTA per matrix, 32 lanes x N / CW warps, rolled pivot loop (gj_roll2d_kernels.cuh), fp32 64 < n <= 128:  X(T, N, CW, MINB)
-// measured on B200, 16 384 x 128x128: CW 32 / 3 CTAs per SM 4.21 ms (default), CW 32 / 2 CTAs 4.25 ms, CW 16 (8 warps) / 2 CTAs 4.87 ms;
+// measured on B200, 16 384 x 128x128: CW 32 / 3 CTAs per SM 4.21 ms (default; 4.14 ms with the two-reduction pivot search), CW 32 / 2 CTAs 4.25 ms, CW 16 (8 warps) / 2 CTAs 4.87 ms;
 // the tile kernel it replaces: 7.08 ms
 #ifndef INVGPU_GJR2_CW
 #define INVGPU_GJR2_CW 32
